@@ -1,0 +1,198 @@
+/*
+ * myfm_b200.h — C ABI of the B200-native Gibbs engine for Bayesian Factorization Machines.
+ *
+ * This is the drop-in boundary for the hot path of tohtsky/myFM (reference paths are relative to
+ * the reference repository root).  The reference has no C ABI of its own: its boundary is the
+ * pybind11 module `myfm._myfm` (cpp_source/declare_module.hpp:67-404).  Each entry point below is
+ * what a binding for that module would call instead of the header-only C++ it calls today; the
+ * file:line each one replaces is cited next to it, and INTEGRATION.md shows the pybind11 stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is HOST memory owned by the caller and may be
+ *    released as soon as the call returns (the engine keeps its own device copies);
+ *  - floating-point data crosses the boundary as float64, as in the reference's Python API
+ *    (src/myfm/base.py:36,285-286); the engine converts to its compute dtype (f32 or f64);
+ *  - sparse matrices are CSR with int64 row pointers and int32 column indices, taken as given
+ *    (indices are neither sorted nor de-duplicated — same as the reference's scipy->Eigen caster);
+ *  - dense matrices V, mu_V, lambda_V are ROW-major: V[j*rank + r], mu_V[g*rank + r] (the shapes
+ *    numpy shows for the reference's FM.V / FMHyperParameters.mu_V);
+ *  - every function returns MYFM_OK or an error code; myfm_last_error() returns the message of
+ *    the last failure on the calling thread.  MYFM_ERR_INVALID_ARGUMENT corresponds to the
+ *    reference's std::invalid_argument (-> ValueError), MYFM_ERR_RUNTIME to std::runtime_error
+ *    (-> RuntimeError);
+ *  - there is NO CPU fallback: a call that needs the GPU fails with MYFM_ERR_CUDA when no sm_100
+ *    device is usable.
+ */
+#ifndef MYFM_B200_H
+#define MYFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MYFM_OK 0
+#define MYFM_ERR_INVALID_ARGUMENT 1
+#define MYFM_ERR_RUNTIME 2
+#define MYFM_ERR_CUDA 3
+
+/* FMLearningConfig::TASKTYPE, include/myfm/FMLearningConfig.hpp:14 */
+#define MYFM_TASK_REGRESSION 0
+#define MYFM_TASK_CLASSIFICATION 1
+#define MYFM_TASK_ORDERED 2
+
+/* compute dtype of the engine (the reference's `Real`: bind.cpp = double, bind_float.cpp = float) */
+#define MYFM_DTYPE_F32 0
+#define MYFM_DTYPE_F64 1
+
+/* RNG contract.
+ * MT19937: the engine consumes the libstdc++ std::mt19937(seed) stream draw for draw in the
+ *          reference's order, so chains are comparable with the reference on
+ *          the same seed.
+ * PHILOX : counter-based device RNG keyed by (seed, iteration, step, index); statistically
+ *          equivalent chain, no host involvement. */
+#define MYFM_RNG_MT19937 0
+#define MYFM_RNG_PHILOX 1
+
+typedef struct myfm_csr {
+  int64_t n_rows;
+  int64_t n_cols;
+  const int64_t *indptr;  /* [n_rows + 1] */
+  const int32_t *indices; /* [nnz] */
+  const double *data;     /* [nnz] */
+} myfm_csr_t;
+
+/* relational::RelationBlock, include/myfm/definitions.hpp:30-52 */
+typedef struct myfm_relation {
+  const int64_t *original_to_block; /* [mapper_size], each in [0, block.n_rows) */
+  int64_t mapper_size;
+  myfm_csr_t block; /* block_size x feature_size */
+} myfm_relation_t;
+
+/* FMLearningConfig, include/myfm/FMLearningConfig.hpp:17-57 (built by ConfigBuilder,
+ * cpp_source/declare_module.hpp:139-156).  Validation happens in myfm_config_validate / at
+ * trainer creation with the reference's messages. */
+typedef struct myfm_config {
+  double alpha_0, beta_0, gamma_0, mu_0, reg_0;
+  int32_t task_type;
+  double nu_oprobit;
+  int32_t fit_w0, fit_linear;
+  int32_t n_iter, n_kept_samples;
+  double cutpoint_scale;
+  const int64_t *group_index; /* [n_group_index] group of every feature (main table then blocks) */
+  int64_t n_group_index;
+  int32_t n_cutpoint_groups;            /* ordered probit only */
+  const int32_t *cutpoint_n_class;      /* [n_cutpoint_groups] */
+  const int64_t *const *cutpoint_index; /* [n_cutpoint_groups] row ids of each group */
+  const int64_t *cutpoint_index_len;    /* [n_cutpoint_groups] */
+} myfm_config_t;
+
+/* Engine options that have no counterpart in the reference. */
+typedef struct myfm_engine_options {
+  int32_t dtype;      /* MYFM_DTYPE_* */
+  int32_t rng;        /* MYFM_RNG_* */
+  int32_t device;     /* CUDA device ordinal */
+  int32_t world_size; /* row-sharded data parallelism: number of ranks (1 = single GPU) */
+  int32_t rank;       /* this process' rank */
+  int64_t row_offset; /* global index of this shard's first training row */
+  int64_t n_rows_global;
+  const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks, or NULL */
+} myfm_engine_options_t;
+
+typedef struct myfm_trainer myfm_trainer_t;
+typedef struct myfm_dataset myfm_dataset_t;
+
+const char *myfm_last_error(void);
+/* Library / device probe: writes the number of usable CUDA devices; never fails without a GPU. */
+int myfm_device_count(int32_t *count);
+/* FMLearningConfig ctor checks, FMLearningConfig.hpp:29-56; writes the number of groups. */
+int myfm_config_validate(const myfm_config_t *cfg, int32_t *n_groups);
+
+/* ---- training: replaces create_train_fm, cpp_source/declare_module.hpp:30-45 ---------------- */
+
+/* GibbsFMTrainer ctor (include/myfm/BaseFMTrainer.hpp:58-105): shape checks, X^T, relation
+ * caches, mt19937(seed); uploads everything to HBM once. */
+int myfm_trainer_create(myfm_trainer_t **out, const myfm_csr_t *X, int32_t n_relations,
+                        const myfm_relation_t *relations, const double *y, int64_t n_y,
+                        int32_t random_seed, const myfm_config_t *cfg,
+                        const myfm_engine_options_t *opt);
+void myfm_trainer_destroy(myfm_trainer_t *t);
+
+/* create_FM + create_Hyper + initialize_hyper + initialize_e (BaseFMTrainer.hpp:107-115,
+ * include/myfm/FM.hpp:34-45, include/myfm/FMTrainer.hpp:89-119). */
+int myfm_trainer_init_fm(myfm_trainer_t *t, int32_t rank, double init_std);
+
+/* n_sweeps x update_all (BaseFMTrainer.hpp:135-152: alpha, w0, lambda_w, mu_w, w, lambda_V,
+ * mu_V, V, e).  Asynchronous for regression; returns once the work is enqueued. */
+int myfm_trainer_step(myfm_trainer_t *t, int32_t n_sweeps);
+int myfm_trainer_sync(myfm_trainer_t *t);
+
+/* Current state (synchronises).  w: [dim_all]; V: [dim_all x rank] row-major. */
+int myfm_trainer_dims(const myfm_trainer_t *t, int64_t *n_train, int64_t *dim_all, int32_t *rank,
+                      int32_t *n_groups);
+int myfm_trainer_get_fm(myfm_trainer_t *t, double *w0, double *w, double *V);
+/* cutpoints of cutpoint group g (ordered probit): [n_class_g - 1] */
+int myfm_trainer_get_cutpoints(myfm_trainer_t *t, int32_t g, double *out);
+/* FMHyperParameters (include/myfm/HyperParams.hpp:8-37); mu_V/lambda_V [n_groups x rank] row-major */
+int myfm_trainer_get_hyper(myfm_trainer_t *t, double *alpha, double *mu_w, double *lambda_w,
+                           double *mu_V, double *lambda_V);
+/* residual cache e_train and factor cache q_train of this shard (tests / diagnostics) */
+int myfm_trainer_get_e(myfm_trainer_t *t, double *e);
+int myfm_trainer_get_q(myfm_trainer_t *t, double *q);
+/* OprobitSampler::accept_count of cutpoint group g (FMTrainer.hpp:83-85) */
+int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count);
+/* number of kernels this trainer has launched so far (bench.py's gpu_launches) */
+int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count);
+/* device milliseconds spent in the dominant kernel family since the last call (CUDA events on
+ * the trainer's stream); family: 0 = column sweeps, 1 = q_init, 2 = e_refresh */
+int myfm_trainer_kernel_ms(myfm_trainer_t *t, int32_t family, double *ms, int64_t *launches);
+/* turn the per-family CUDA-event timing on or off (off by default; adds two event records per
+ * launch group when on) */
+int myfm_trainer_set_profiling(myfm_trainer_t *t, int32_t on);
+
+/* ---- prediction: replaces FM::predict_score / Predictor::predict* ---------------------------- */
+
+/* A design matrix (+ relation blocks) resident on the device, reusable across calls. */
+int myfm_dataset_create(myfm_dataset_t **out, const myfm_csr_t *X, int32_t n_relations,
+                        const myfm_relation_t *relations, int32_t dtype, int32_t device);
+void myfm_dataset_destroy(myfm_dataset_t *d);
+
+/* FM::predict_score (include/myfm/FM.hpp:47-136) for one sample given on the host.
+ * out: [n_rows].  dim_all must equal the dataset's total feature size (else INVALID_ARGUMENT). */
+int myfm_predict_score(const myfm_dataset_t *d, double w0, const double *w, const double *V,
+                       int64_t dim_all, int32_t rank, double *out);
+
+/* Predictor::predict / predict_parallel (include/myfm/predictor.hpp:35-76,126-147): mean over
+ * n_samples of score (REGRESSION) or Phi(score) (CLASSIFICATION).  w0s [n_samples],
+ * ws [n_samples x dim_all], Vs [n_samples x dim_all x rank].  out: [n_rows]. */
+int myfm_predict_mean(const myfm_dataset_t *d, int32_t task_type, int32_t n_samples,
+                      const double *w0s, const double *ws, const double *Vs, int64_t dim_all,
+                      int32_t rank, double *out);
+
+/* FM::oprobit_predict_proba averaged over samples (predictor.hpp:78-124, FM.hpp:137-162).
+ * cutpoints: [n_samples x n_cpt]; out: [n_rows x (n_cpt + 1)] row-major. */
+int myfm_predict_oprobit_mean(const myfm_dataset_t *d, int32_t n_samples, const double *w0s,
+                              const double *ws, const double *Vs, const double *cutpoints,
+                              int32_t n_cpt, int64_t dim_all, int32_t rank, double *out);
+
+/* FM::predict_score with the trainer's CURRENT device-resident sample (no weight upload); used
+ * by per-iteration callbacks (src/myfm/utils/callbacks/libfm.py:82-113). */
+int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, double *out);
+
+/* ---- host-side pieces that run without a GPU (exercised by the CPU test-suite) -------------- */
+
+/* The engine's MT19937 variate stream for one regression sweep layout: fills `out` with the
+ * standardised variates the device consumes, in stream order. */
+int myfm_rng_fill(int32_t dtype, int32_t seed, int64_t n_skip_normals_persistent,
+                  const int32_t *kinds, const double *shapes, int64_t n, double *out);
+
+/* Dependency-level schedule of the columns of a CSR matrix: level[j] for
+ * every column; columns of one level are pairwise row-disjoint and running levels in order
+ * reproduces the reference's serial column order exactly.  Returns the number of levels. */
+int myfm_level_schedule(const myfm_csr_t *X, int32_t *level, int32_t *n_levels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYFM_B200_H */

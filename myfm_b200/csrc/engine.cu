@@ -1,0 +1,1134 @@
+// myfm_b200 engine: device-resident Gibbs trainer, prediction datasets and the C ABI
+// (include/myfm_b200.h).  One CUDA stream per trainer; data is uploaded once and a whole
+// regression sweep runs without any host round trip.
+#include "../../include/myfm_b200.h"
+
+#include "common.cuh"
+#include "host_data.hpp"
+#include "kernels.cuh"
+#include "rng.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+namespace myfm {
+
+namespace {
+thread_local std::string g_last_error;
+
+constexpr int LONG_COLUMN = 2048; // columns longer than this get a whole thread block
+constexpr int REDUCE_BLOCKS = 592; // 4 x 148 SMs
+
+int pow2_ceil_clamped(double x, int lo, int hi) {
+  int v = lo;
+  while (v < hi && v < x)
+    v <<= 1;
+  return v;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+template <typename Real> struct DevCs {
+  int64_t n_major = 0, n_minor = 0, nnz = 0;
+  DevBuf<int> ptr, idx;
+  DevBuf<Real> val;
+  void upload(const HostCs<Real> &h, cudaStream_t s) {
+    n_major = h.n_major, n_minor = h.n_minor, nnz = h.nnz();
+    ptr.upload(h.ptr, s);
+    idx.upload(h.idx, s);
+    val.upload(h.val, s);
+  }
+  CsView<Real> view() const { return CsView<Real>{ptr.p, idx.p, val.p}; }
+  double avg_len() const { return n_major ? static_cast<double>(nnz) / n_major : 0.0; }
+};
+
+// Kernel timing by family with CUDA events on the launching stream (bench.py's roofline leg).
+struct KernelTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Span {
+    int family;
+    size_t a, b;
+  };
+  std::vector<Span> spans;
+  double ms[3] = {0, 0, 0};
+  int64_t launches[3] = {0, 0, 0};
+  ~KernelTimer() {
+    for (auto e : pool)
+      cudaEventDestroy(e);
+  }
+  size_t mark(cudaStream_t s) {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      MYFM_CUDA(cudaEventCreate(&e));
+      pool.push_back(e);
+    }
+    MYFM_CUDA(cudaEventRecord(pool[used], s));
+    return used++;
+  }
+  void collect() { // caller has synchronised the stream
+    for (auto &sp : spans) {
+      float t = 0;
+      MYFM_CUDA(cudaEventElapsedTime(&t, pool[sp.a], pool[sp.b]));
+      ms[sp.family] += t;
+      launches[sp.family]++;
+    }
+    spans.clear();
+    used = 0;
+  }
+};
+
+// Design matrix + relation blocks on the device, with the per-block tables of the forward pass.
+template <typename Real> struct DevRelationData {
+  int64_t S = 0, F = 0, offset = 0;
+  DevCs<Real> B; // CSR of the block
+  DevBuf<int> map;
+  DevBuf<Real> tab_lin, tab_q, tab_qs;
+};
+
+struct DatasetBase {
+  virtual ~DatasetBase() = default;
+  int dtype = MYFM_DTYPE_F32;
+  int device = 0;
+  int64_t n_rows = 0, dim_main = 0, dim_all = 0;
+};
+
+template <typename Real> struct Dataset : DatasetBase {
+  DevCs<Real> X;
+  std::vector<DevRelationData<Real>> rels;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t *launch_counter = nullptr;
+  int64_t own_counter = 0;
+  // scratch for host-supplied samples
+  DevBuf<Real> w, Vt, w0, score, accum, cutp;
+
+  ~Dataset() override {
+    if (own_stream && stream)
+      cudaStreamDestroy(stream);
+  }
+
+  void count(int n = 1) { (launch_counter ? *launch_counter : own_counter) += n; }
+
+  // Shape checks of util.hpp:147-165 / definitions.hpp:38-41, then upload.
+  void build(const HostCs<Real> &Xh, int n_rel, const myfm_relation_t *relations, cudaStream_t s) {
+    stream = s;
+    n_rows = Xh.n_major;
+    dim_main = Xh.n_minor;
+    dim_all = dim_main;
+    X.upload(Xh, s);
+    if (n_rel > MAX_REL)
+      throw std::invalid_argument("too many relation blocks (at most 8 are supported).");
+    rels.resize(n_rel);
+    for (int b = 0; b < n_rel; b++) {
+      const myfm_relation_t &r = relations[b];
+      if (n_rows != r.mapper_size) {
+        std::ostringstream ss;
+        ss << "main table has size " << n_rows << " but the relation[" << b << "] has size "
+           << r.mapper_size;
+        throw std::runtime_error(ss.str());
+      }
+      HostCs<Real> Bh = host_from_api<Real>(r.block, "relation block");
+      std::vector<int> map(r.mapper_size);
+      for (int64_t i = 0; i < r.mapper_size; i++) {
+        if (r.original_to_block[i] < 0 || r.original_to_block[i] >= Bh.n_major)
+          throw std::runtime_error("index mapping points to non-existing row.");
+        map[i] = static_cast<int>(r.original_to_block[i]);
+      }
+      DevRelationData<Real> &d = rels[b];
+      d.S = Bh.n_major, d.F = Bh.n_minor, d.offset = dim_all;
+      d.B.upload(Bh, s);
+      d.map.upload(map, s);
+      dim_all += d.F;
+    }
+    MYFM_CUDA(cudaStreamSynchronize(s)); // host staging vectors die here
+  }
+
+  void ensure_tables(int K) {
+    for (auto &d : rels) {
+      if (d.tab_lin.n < static_cast<size_t>(d.S))
+        d.tab_lin.alloc(d.S);
+      if (d.tab_q.n < static_cast<size_t>(d.S) * K) {
+        d.tab_q.alloc(static_cast<size_t>(d.S) * K);
+        d.tab_qs.alloc(static_cast<size_t>(d.S) * K);
+      }
+    }
+  }
+
+  // out = predict_score(X, rels) [- y]; FM.hpp:54-136 with all factors fused in one CSR pass.
+  void predict(const Real *w_dev, const Real *Vt_dev, int K, const Real *w0_dev, const Real *y,
+               Real *out) {
+    ensure_tables(K);
+    RelPredictPack<Real> pack;
+    pack.n = static_cast<int>(rels.size());
+    for (int b = 0; b < pack.n; b++) {
+      auto &d = rels[b];
+      if (d.S) {
+        k_block_tables<Real><<<ceil_div(d.S * 32, 256), 256, 0, stream>>>(
+            static_cast<int>(d.S), d.B.view(), w_dev, Vt_dev, K, static_cast<int>(d.offset),
+            d.tab_lin.p, d.tab_q.p, d.tab_qs.p);
+        count();
+      }
+      pack.r[b] = RelPredictView<Real>{d.map.p, d.tab_lin.p, d.tab_q.p, d.tab_qs.p};
+    }
+    if (!n_rows)
+      return;
+    const int lpr = pow2_ceil_clamped(K / 4.0, 1, 32);
+    const int n = static_cast<int>(n_rows);
+#define MYFM_PREDICT(L)                                                                            \
+  case L:                                                                                          \
+    k_predict<Real, L><<<ceil_div(static_cast<int64_t>(n) * L, 256), 256, 0, stream>>>(            \
+        n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out);                                      \
+    break;
+    switch (lpr) {
+      MYFM_PREDICT(1)
+      MYFM_PREDICT(2)
+      MYFM_PREDICT(4)
+      MYFM_PREDICT(8)
+      MYFM_PREDICT(16)
+      MYFM_PREDICT(32)
+    }
+#undef MYFM_PREDICT
+    count();
+    MYFM_CUDA(cudaGetLastError());
+  }
+
+  // Stage one host sample (float64, V row-major) into the scratch buffers.
+  void stage_sample(double w0_h, const double *w_h, const double *V_h, int K) {
+    std::vector<Real> wv(dim_all), Vv(static_cast<size_t>(dim_all) * K);
+    for (int64_t i = 0; i < dim_all; i++)
+      wv[i] = static_cast<Real>(w_h[i]);
+    for (size_t i = 0; i < Vv.size(); i++)
+      Vv[i] = static_cast<Real>(V_h[i]);
+    Real w0v = static_cast<Real>(w0_h);
+    w.upload(wv, stream);
+    Vt.upload(Vv, stream);
+    w0.upload(&w0v, 1, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  void check_dim(int64_t given) const { // FM.hpp:66-72 / predictor.hpp:24-33
+    if (given != dim_all) {
+      std::ostringstream ss;
+      ss << "Total feature size mismatch. Should be " << given << ", but got " << dim_all << ".";
+      throw std::invalid_argument(ss.str());
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Trainer
+// ------------------------------------------------------------------------------------------------
+struct TrainerBase {
+  virtual ~TrainerBase() = default;
+  virtual void init_fm(int rank, double init_std) = 0;
+  virtual void step(int n) = 0;
+  virtual void sync() = 0;
+  virtual void dims(int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) const = 0;
+  virtual void get_fm(double *w0, double *w, double *V) = 0;
+  virtual void get_cutpoints(int g, double *out) = 0;
+  virtual void get_hyper(double *alpha, double *mu_w, double *lambda_w, double *mu_V,
+                         double *lambda_V) = 0;
+  virtual void get_e(double *e) = 0;
+  virtual void get_q(double *q) = 0;
+  virtual int64_t mh_accept(int g) = 0;
+  virtual int64_t launch_count() const = 0;
+  virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
+  virtual void set_profiling(bool on) = 0;
+  virtual void predict_score(DatasetBase *d, double *out) = 0;
+  int dtype = MYFM_DTYPE_F32;
+};
+
+template <typename Real> struct DevRelationTrain {
+  DevCs<Real> Bt; // CSC of the block
+  DevBuf<int> seg_ptr, seg_rows;
+  DevBuf<Real> card, q, q_S, c, c_S, e, e_q;
+  int n_levels = 0;
+  DevBuf<int> level_ptr, level_cols;
+  RelCache<Real> cache() { return RelCache<Real>{card.p, q.p, q_S.p, c.p, c_S.p, e.p, e_q.p}; }
+};
+
+template <typename Real> struct Trainer : TrainerBase {
+  Config cfg;
+  myfm_engine_options_t opt;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  KernelTimer timer;
+
+  Dataset<Real> data; // main table CSR + relation blocks (CSR, map, forward tables)
+  DevCs<Real> Xt;     // CSC of the main table
+  LevelPlan plan;
+  DevBuf<int> plan_cols;
+  std::vector<DevRelationTrain<Real>> rel_train;
+
+  int64_t N = 0, D = 0, D_all = 0;
+  int K = -1, G = 0;
+  std::vector<Real> y_host;
+  DevBuf<Real> y, e, q;
+  DevBuf<Real> w, V, Vt;       // V column-major [D_all x K]; Vt feature-major mirror
+  DevBuf<Real> hyper;          // alpha, w0, mu_w[G], lambda_w[G], mu_V[G*K], lambda_V[G*K]
+  DevBuf<Real> scal;           // [0] = w0 delta
+  DevBuf<Real> partial;        // grid-reduction partials
+  DevBuf<int> group, feat_ptr, feat_idx;
+
+  MtStream<Real> rng;
+  SweepLayout layout;
+  DevBuf<Real> z_dev;
+  PinnedBuf<Real> z_pinned[2];
+  cudaEvent_t z_copied[2] = {nullptr, nullptr};
+  int64_t sweep_index = 0;
+  std::vector<Real> shapes_lw; // gamma shape per group
+  Real shape_alpha = 0;
+  std::vector<Real> e_host;
+
+  Trainer(const myfm_csr_t &X_api, int n_rel, const myfm_relation_t *relations, const double *y_api,
+          int64_t n_y, int seed, const myfm_config_t &cfg_api, const myfm_engine_options_t &o)
+      : cfg(cfg_api), opt(o), device(o.device), rng(seed) {
+    dtype = o.dtype;
+    if (o.rng != MYFM_RNG_MT19937)
+      throw std::runtime_error("rng=philox is not available in this build; use rng=mt19937.");
+    if (o.world_size > 1)
+      throw std::runtime_error("row-sharded multi-GPU training is not available in this build.");
+    if (cfg.task_type == MYFM_TASK_ORDERED)
+      throw std::runtime_error("ordered probit is not available in this build.");
+    HostCs<Real> Xh = host_from_api<Real>(X_api, "X");
+    if (Xh.n_major != n_y) { // BaseFMTrainer.hpp:69-76
+      std::ostringstream ss;
+      ss << "Shape mismatch: X has size " << Xh.n_major << " and y has size " << n_y;
+      throw std::runtime_error(ss.str());
+    }
+    if (has_duplicate_entries(Xh))
+      throw std::invalid_argument(
+          "X lists the same (row, column) twice; sum duplicates first (X.sum_duplicates()).");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device)
+      throw CudaError("no usable CUDA device: the myfm_b200 engine has no CPU fallback.");
+    MYFM_CUDA(cudaSetDevice(device));
+    MYFM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto &ev : z_copied)
+      MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+
+    data.launch_counter = &launches;
+    data.build(Xh, n_rel, relations, stream);
+    N = data.n_rows, D = data.dim_main, D_all = data.dim_all;
+    if (static_cast<int64_t>(cfg.group_index.size()) != D_all)
+      throw std::invalid_argument("group_index must have one entry per feature.");
+    G = cfg.n_groups;
+
+    HostCs<Real> Xth = host_transpose(Xh);
+    Xt.upload(Xth, stream);
+    plan = make_level_plan(Xth, LONG_COLUMN);
+    plan_cols.upload(plan.cols, stream);
+
+    rel_train.resize(n_rel);
+    for (int b = 0; b < n_rel; b++) {
+      const myfm_relation_t &r = relations[b];
+      HostCs<Real> Bh = host_from_api<Real>(r.block, "relation block");
+      if (has_duplicate_entries(Bh))
+        throw std::invalid_argument("a relation block lists the same (row, column) twice.");
+      HostCs<Real> Bth = host_transpose(Bh);
+      DevRelationTrain<Real> &t = rel_train[b];
+      t.Bt.upload(Bth, stream);
+      const int64_t S = Bh.n_major;
+      // rows grouped by block row, ascending (segment sums replace the reference's serial
+      // accumulation, definitions.hpp:64-66 / FMTrainer.hpp:270-274)
+      std::vector<int> seg_ptr(S + 1, 0), seg_rows(N);
+      std::vector<Real> card(S, Real(0));
+      for (int64_t i = 0; i < N; i++) {
+        seg_ptr[r.original_to_block[i] + 1]++;
+        card[r.original_to_block[i]]++;
+      }
+      for (int64_t s = 0; s < S; s++)
+        seg_ptr[s + 1] += seg_ptr[s];
+      std::vector<int> cur(seg_ptr.begin(), seg_ptr.end() - 1);
+      for (int64_t i = 0; i < N; i++)
+        seg_rows[cur[r.original_to_block[i]]++] = static_cast<int>(i);
+      t.seg_ptr.upload(seg_ptr, stream);
+      t.seg_rows.upload(seg_rows, stream);
+      t.card.upload(card, stream);
+      for (DevBuf<Real> *buf : {&t.q, &t.q_S, &t.c, &t.c_S, &t.e, &t.e_q}) {
+        buf->alloc(S);
+        buf->zero(stream);
+      }
+      LevelPlan bp = make_level_plan(Bth, std::numeric_limits<int>::max());
+      t.n_levels = bp.n_levels;
+      t.level_ptr.upload(bp.level_ptr, stream);
+      t.level_cols.upload(bp.cols, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    y_host.resize(N);
+    for (int64_t i = 0; i < N; i++)
+      y_host[i] = static_cast<Real>(y_api[i]);
+    y.upload(y_host, stream);
+    e.alloc(N);
+    q.alloc(N);
+    group.upload(cfg.group_index, stream);
+    feat_ptr.upload(cfg.feat_ptr, stream);
+    feat_idx.upload(cfg.feat_idx, stream);
+    partial.alloc(REDUCE_BLOCKS);
+    scal.alloc(4);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+
+    // Gamma shapes are data independent (FMTrainer.hpp:140,157)
+    shape_alpha = (static_cast<Real>(cfg.alpha_0) + N) / 2;
+    shapes_lw.resize(G);
+    for (int g = 0; g < G; g++) {
+      Real a = static_cast<Real>(cfg.alpha_0) + static_cast<size_t>(cfg.feat_ptr[g + 1] - cfg.feat_ptr[g]);
+      shapes_lw[g] = a / 2;
+    }
+  }
+
+  ~Trainer() override {
+    if (stream)
+      cudaStreamSynchronize(stream);
+    for (auto ev : z_copied)
+      if (ev)
+        cudaEventDestroy(ev);
+    if (stream)
+      cudaStreamDestroy(stream);
+  }
+
+  HyperView<Real> hv() {
+    Real *h = hyper.p;
+    return HyperView<Real>{h, h + 1, h + 2, h + 2 + G, h + 2 + 2 * G,
+                           h + 2 + 2 * G + static_cast<size_t>(G) * K};
+  }
+  size_t hyper_size() const { return 2 + 2 * static_cast<size_t>(G) + 2 * static_cast<size_t>(G) * K; }
+
+  void launched(int n = 1) { launches += n; }
+
+  // create_FM + create_Hyper (BaseFMTrainer.hpp:107-115), initialize_hyper + initialize_e
+  // (FMTrainer.hpp:89-119)
+  void init_fm(int rank, double init_std) override {
+    if (rank < 0)
+      throw std::invalid_argument("rank must be non-negative.");
+    MYFM_CUDA(cudaSetDevice(device));
+    K = rank;
+    std::vector<Real> Vh(static_cast<size_t>(D_all) * K), wh(D_all);
+    Real w0h = 0;
+    rng.init_weights(Vh.data(), Vh.size(), wh.data(), wh.size(), &w0h, static_cast<Real>(init_std));
+    V.alloc(Vh.size());
+    Vt.alloc(Vh.size());
+    V.upload(Vh, stream);
+    w.upload(wh, stream);
+    if (Vh.size()) {
+      k_transpose_V<Real><<<ceil_div(Vh.size(), 256), 256, 0, stream>>>(D_all, K, V.p, Vt.p);
+      launched();
+    }
+    std::vector<Real> hh(hyper_size());
+    hh[0] = static_cast<Real>(1); // alpha
+    hh[1] = w0h;
+    for (int g = 0; g < G; g++)
+      hh[2 + g] = static_cast<Real>(0), hh[2 + G + g] = static_cast<Real>(1e-5);
+    for (size_t i = 0; i < static_cast<size_t>(G) * K; i++)
+      hh[2 + 2 * G + i] = static_cast<Real>(0),
+                     hh[2 + 2 * G + static_cast<size_t>(G) * K + i] = static_cast<Real>(1e-5);
+    hyper.upload(hh, stream);
+    layout = SweepLayout::make(cfg.task_type == MYFM_TASK_REGRESSION, cfg.fit_w0, cfg.fit_linear, G,
+                               K, D_all);
+    z_dev.alloc(layout.total);
+    for (auto &pb : z_pinned)
+      pb.alloc(layout.total);
+    data.predict(w.p, Vt.p, K, hv().w0, y.p, e.p);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    sweep_index = 0;
+  }
+
+  // Standardised variates of one sweep, in the reference's consumption order.
+  void draw_sweep_variates(Real *out) {
+    const SweepLayout &L = layout;
+    if (L.g_alpha >= 0)
+      out[L.g_alpha] = rng.gamma(shape_alpha);
+    if (L.z_w0 >= 0)
+      out[L.z_w0] = rng.normal();
+    for (int g = 0; g < G; g++)
+      out[L.g_lw + g] = rng.gamma(shapes_lw[g]);
+    for (int g = 0; g < G; g++)
+      out[L.z_mw + g] = rng.normal();
+    if (L.z_w >= 0)
+      for (int64_t j = 0; j < D_all; j++)
+        out[L.z_w + j] = rng.normal();
+    for (int r = 0; r < K; r++)
+      for (int g = 0; g < G; g++)
+        out[L.g_lV + static_cast<int64_t>(r) * G + g] = rng.gamma(shapes_lw[g]);
+    for (int64_t i = 0; i < static_cast<int64_t>(K) * G; i++)
+      out[L.z_mV + i] = rng.normal();
+    for (int64_t i = 0; i < static_cast<int64_t>(K) * D_all; i++)
+      out[L.z_V + i] = rng.normal();
+  }
+
+  struct TimedSpan {
+    KernelTimer &t;
+    cudaStream_t s;
+    int family;
+    size_t a = 0;
+    TimedSpan(KernelTimer &t_, cudaStream_t s_, int f) : t(t_), s(s_), family(f) {
+      if (t.enabled)
+        a = t.mark(s);
+    }
+    ~TimedSpan() {
+      if (t.enabled) {
+        size_t b = t.mark(s);
+        t.spans.push_back({family, a, b});
+      }
+    }
+  };
+
+  // One level-ordered sweep over the main-table columns (w or one factor of V).
+  template <bool IS_V>
+  void sweep_main(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda,
+                  const Real *mu) {
+    SweepArgs<Real> a;
+    a.Xt = Xt.view();
+    a.e = e.p, a.q = q.p;
+    a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
+    a.z = z, a.group = group.p;
+    a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
+    for (int lv = 0; lv < plan.n_levels; lv++) {
+      const int base = plan.level_ptr[lv], n = plan.level_ptr[lv + 1] - base;
+      const int n_long = plan.n_long[lv], n_short = n - n_long;
+      TimedSpan span(timer, stream, 0);
+      if (n_long) {
+        a.cols = plan_cols.p + base, a.n_cols = n_long;
+        k_sweep_block<Real, IS_V><<<n_long, 512, 0, stream>>>(a);
+        launched();
+      }
+      if (n_short) {
+        a.cols = plan_cols.p + base + n_long, a.n_cols = n_short;
+        k_sweep_warp<Real, IS_V><<<ceil_div(static_cast<int64_t>(n_short) * 32, 256), 256, 0, stream>>>(a);
+        launched();
+      }
+    }
+  }
+
+  void spmv(const DevCs<Real> &A, const Real *x, Real *out, bool squared) {
+    if (!A.n_major)
+      return;
+    const int lpr = pow2_ceil_clamped(A.avg_len() / 4.0, 1, 32);
+    const int n = static_cast<int>(A.n_major);
+    const int grid = ceil_div(static_cast<int64_t>(n) * lpr, 256);
+#define MYFM_SPMV(L)                                                                               \
+  case L:                                                                                          \
+    if (squared)                                                                                   \
+      k_spmv<Real, L, true><<<grid, 256, 0, stream>>>(n, A.view(), x, out);                        \
+    else                                                                                           \
+      k_spmv<Real, L, false><<<grid, 256, 0, stream>>>(n, A.view(), x, out);                       \
+    break;
+    switch (lpr) {
+      MYFM_SPMV(1)
+      MYFM_SPMV(2)
+      MYFM_SPMV(4)
+      MYFM_SPMV(8)
+      MYFM_SPMV(16)
+      MYFM_SPMV(32)
+    }
+#undef MYFM_SPMV
+    launched();
+  }
+
+  template <bool IS_V>
+  void rel_sweep(int b, Real *theta, Real *theta_t, int64_t t_stride, const Real *z,
+                 const Real *lambda, const Real *mu) {
+    auto &d = data.rels[b];
+    auto &t = rel_train[b];
+    if (!d.F)
+      return;
+    RelSweepArgs<Real> a;
+    a.Bt = t.Bt.view();
+    a.n_levels = t.n_levels, a.level_ptr = t.level_ptr.p, a.level_cols = t.level_cols.p;
+    a.cache = t.cache();
+    a.theta = theta + d.offset;
+    a.theta_t = theta_t ? theta_t + d.offset * t_stride : nullptr;
+    a.t_stride = t_stride;
+    a.z = z + d.offset, a.group = group.p + d.offset;
+    a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
+    k_rel_sweep<Real, IS_V><<<1, 1024, 0, stream>>>(a);
+    launched();
+  }
+
+  // update_w (FMTrainer.hpp:231-314)
+  void update_w(const Real *z) {
+    HyperView<Real> h = hv();
+    if (!cfg.fit_linear) {
+      w.zero(stream); // e keeps the stale contribution until update_e, as in the reference
+      return;
+    }
+    sweep_main<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
+    const int n = static_cast<int>(N);
+    for (size_t b = 0; b < data.rels.size(); b++) {
+      auto &d = data.rels[b];
+      auto &t = rel_train[b];
+      spmv(d.B, w.p + d.offset, t.q.p, false);
+      if (d.S) {
+        k_rel_gather_w<Real><<<ceil_div(d.S * 32, 256), 256, 0, stream>>>(
+            static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), e.p);
+        launched();
+      }
+      rel_sweep<false>(static_cast<int>(b), w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
+      spmv(d.B, w.p + d.offset, t.q.p, false);
+      if (n) {
+        k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, e.p);
+        launched();
+      }
+    }
+  }
+
+  // update_V (FMTrainer.hpp:316-486)
+  void update_V(const Real *z_all) {
+    HyperView<Real> h = hv();
+    const int n = static_cast<int>(N);
+    for (int r = 0; r < K; r++) {
+      Real *Vr = V.p + static_cast<size_t>(D_all) * r;
+      const Real *z = z_all + static_cast<size_t>(D_all) * r;
+      const Real *lam = h.lambda_V + static_cast<size_t>(G) * r, *mu = h.mu_V + static_cast<size_t>(G) * r;
+      {
+        TimedSpan span(timer, stream, 1);
+        if (D)
+          spmv(data.X, Vr, q.p, false);
+        else
+          q.zero(stream);
+        for (size_t b = 0; b < data.rels.size(); b++) {
+          auto &d = data.rels[b];
+          auto &t = rel_train[b];
+          spmv(d.B, Vr + d.offset, t.q.p, false);
+          if (n) {
+            k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, q.p);
+            launched();
+          }
+        }
+      }
+      sweep_main<true>(Vr, Vt.p + r, K, z, lam, mu);
+      for (size_t b = 0; b < data.rels.size(); b++) {
+        auto &d = data.rels[b];
+        auto &t = rel_train[b];
+        spmv(d.B, Vr + d.offset, t.q_S.p, true);
+        if (d.S) {
+          k_rel_gather_v<Real><<<ceil_div(d.S * 32, 256), 256, 0, stream>>>(
+              static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), e.p, q.p);
+          launched();
+        }
+        rel_sweep<true>(static_cast<int>(b), Vr, Vt.p + r, K, z, lam, mu);
+        if (n) {
+          k_rel_resync_v<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.cache(), e.p, q.p);
+          launched();
+        }
+      }
+    }
+  }
+
+  // update_e for classification (FMTrainer.hpp:498-512): the truncated-normal draws consume the
+  // mt19937 stream row by row, data dependently, so in MT19937 mode they run on the host.
+  void classification_latent() {
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    e_host.resize(N);
+    e.download(e_host.data(), N, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    const Real zero = 0, sd = 1;
+    for (int64_t i = 0; i < N; i++) {
+      Real pred = e_host[i];
+      Real n = y_host[i] > 0 ? rng.tn_left(pred, sd, zero) : rng.tn_right(pred, sd, zero);
+      e_host[i] -= n;
+    }
+    e.upload(e_host.data(), N, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // update_all (BaseFMTrainer.hpp:135-152)
+  void sweep() {
+    const int slot = static_cast<int>(sweep_index & 1);
+    if (sweep_index >= 2)
+      MYFM_CUDA(cudaEventSynchronize(z_copied[slot]));
+    draw_sweep_variates(z_pinned[slot].p);
+    MYFM_CUDA(cudaMemcpyAsync(z_dev.p, z_pinned[slot].p, layout.total * sizeof(Real),
+                              cudaMemcpyHostToDevice, stream));
+    MYFM_CUDA(cudaEventRecord(z_copied[slot], stream));
+    const Real *z = z_dev.p;
+    HyperView<Real> h = hv();
+    const SweepLayout &L = layout;
+
+    if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
+      k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, e.p, h.w0, partial.p);
+      k_finish_alpha<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p,
+                                                   static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha);
+      launched(2);
+    }
+    if (cfg.fit_w0) { // update_w0
+      k_reduce_e<Real, 1><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, e.p, h.w0, partial.p);
+      k_finish_w0<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p, static_cast<int>(N),
+                                                static_cast<Real>(cfg.reg_0), h.alpha, z + L.z_w0, h.w0,
+                                                scal.p);
+      k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, e.p, scal.p);
+      launched(3);
+    } else {
+      MYFM_CUDA(cudaMemsetAsync(h.w0, 0, sizeof(Real), stream));
+    }
+    if (G) { // update_lambda_w, update_mu_w
+      k_group_hyper<Real><<<G, 256, 0, stream>>>(G, feat_ptr.p, feat_idx.p, w.p, 0, h.mu_w, h.lambda_w,
+                                                 z + L.g_lw, z + L.z_mw, static_cast<Real>(cfg.beta_0),
+                                                 static_cast<Real>(cfg.gamma_0), static_cast<Real>(cfg.mu_0));
+      launched();
+    }
+    update_w(L.z_w >= 0 ? z + L.z_w : nullptr);
+    if (G && K) { // update_lambda_V, update_mu_V
+      k_group_hyper<Real><<<G * K, 256, 0, stream>>>(G, feat_ptr.p, feat_idx.p, V.p, D_all, h.mu_V,
+                                                     h.lambda_V, z + L.g_lV, z + L.z_mV,
+                                                     static_cast<Real>(cfg.beta_0), static_cast<Real>(cfg.gamma_0),
+                                                     static_cast<Real>(cfg.mu_0));
+      launched();
+    }
+    update_V(z + L.z_V);
+    { // update_e
+      TimedSpan span(timer, stream, 2);
+      data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e.p);
+    }
+    if (cfg.task_type == MYFM_TASK_CLASSIFICATION)
+      classification_latent();
+    MYFM_CUDA(cudaGetLastError());
+    sweep_index++;
+  }
+
+  void require_fm() const {
+    if (K < 0)
+      throw std::runtime_error("myfm_trainer_init_fm must be called first.");
+  }
+
+  void step(int n) override {
+    require_fm();
+    MYFM_CUDA(cudaSetDevice(device));
+    for (int i = 0; i < n; i++)
+      sweep();
+  }
+  void sync() override {
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    if (timer.enabled)
+      timer.collect();
+  }
+  void dims(int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) const override {
+    *n_train = N, *dim_all = D_all, *rank = K, *n_groups = G;
+  }
+
+  template <typename T> std::vector<T> fetch(const T *dev, size_t n) {
+    std::vector<T> h(n);
+    if (n)
+      MYFM_CUDA(cudaMemcpyAsync(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    return h;
+  }
+
+  void get_fm(double *w0_out, double *w_out, double *V_out) override {
+    require_fm();
+    auto hh = fetch(hyper.p, 2);
+    auto wh = fetch(w.p, D_all);
+    auto Vh = fetch(Vt.p, static_cast<size_t>(D_all) * K);
+    *w0_out = hh[1];
+    for (int64_t i = 0; i < D_all; i++)
+      w_out[i] = wh[i];
+    for (size_t i = 0; i < Vh.size(); i++)
+      V_out[i] = Vh[i];
+  }
+  void get_cutpoints(int, double *) override { throw std::runtime_error("No cutpoint available for this FM."); }
+  void get_hyper(double *alpha, double *mu_w, double *lambda_w, double *mu_V, double *lambda_V) override {
+    require_fm();
+    auto hh = fetch(hyper.p, hyper_size());
+    *alpha = hh[0];
+    for (int g = 0; g < G; g++)
+      mu_w[g] = hh[2 + g], lambda_w[g] = hh[2 + G + g];
+    const Real *mv = hh.data() + 2 + 2 * G, *lv = mv + static_cast<size_t>(G) * K;
+    for (int g = 0; g < G; g++)
+      for (int r = 0; r < K; r++) // device: g + G*r  ->  boundary: g*K + r
+        mu_V[static_cast<size_t>(g) * K + r] = mv[g + static_cast<size_t>(G) * r],
+                                    lambda_V[static_cast<size_t>(g) * K + r] = lv[g + static_cast<size_t>(G) * r];
+  }
+  void get_e(double *out) override {
+    auto h = fetch(e.p, N);
+    for (int64_t i = 0; i < N; i++)
+      out[i] = h[i];
+  }
+  void get_q(double *out) override {
+    auto h = fetch(q.p, N);
+    for (int64_t i = 0; i < N; i++)
+      out[i] = h[i];
+  }
+  int64_t mh_accept(int) override { return 0; }
+  int64_t launch_count() const override { return launches; }
+  void kernel_ms(int family, double *ms, int64_t *n) override {
+    sync();
+    if (family < 0 || family > 2)
+      throw std::invalid_argument("kernel family must be 0, 1 or 2.");
+    *ms = timer.ms[family], *n = timer.launches[family];
+    timer.ms[family] = 0, timer.launches[family] = 0;
+  }
+  void set_profiling(bool on) override {
+    sync();
+    timer.enabled = on;
+  }
+  void predict_score(DatasetBase *db, double *out) override {
+    require_fm();
+    if (db->dtype != dtype)
+      throw std::invalid_argument("dataset and trainer use different compute dtypes.");
+    auto *d = static_cast<Dataset<Real> *>(db);
+    d->check_dim(D_all);
+    MYFM_CUDA(cudaStreamSynchronize(stream)); // the sample must be final before another stream reads it
+    if (d->score.n < static_cast<size_t>(d->n_rows))
+      d->score.alloc(d->n_rows);
+    d->predict(w.p, Vt.p, K, hv().w0, nullptr, d->score.p);
+    std::vector<Real> h(d->n_rows);
+    d->score.download(h.data(), d->n_rows, d->stream);
+    MYFM_CUDA(cudaStreamSynchronize(d->stream));
+    for (int64_t i = 0; i < d->n_rows; i++)
+      out[i] = h[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// prediction over host-supplied samples
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+void dataset_predict_score(Dataset<Real> &d, double w0, const double *w, const double *V, int64_t dim_all,
+                           int K, double *out) {
+  d.check_dim(dim_all);
+  MYFM_CUDA(cudaSetDevice(d.device));
+  d.stage_sample(w0, w, V, K);
+  if (d.score.n < static_cast<size_t>(d.n_rows))
+    d.score.alloc(d.n_rows);
+  d.predict(d.w.p, d.Vt.p, K, d.w0.p, nullptr, d.score.p);
+  std::vector<Real> h(d.n_rows);
+  d.score.download(h.data(), d.n_rows, d.stream);
+  MYFM_CUDA(cudaStreamSynchronize(d.stream));
+  for (int64_t i = 0; i < d.n_rows; i++)
+    out[i] = h[i];
+}
+
+// predictor.hpp:126-147 (and :35-76, same arithmetic) / :78-124 with n_cpt >= 0
+template <typename Real>
+void dataset_predict_mean(Dataset<Real> &d, int task, int n_samples, const double *w0s, const double *ws,
+                          const double *Vs, const double *cutpoints, int n_cpt, int64_t dim_all, int K,
+                          double *out) {
+  d.check_dim(dim_all);
+  if (n_samples <= 0)
+    throw std::runtime_error("Told to predict but no sample available.");
+  MYFM_CUDA(cudaSetDevice(d.device));
+  const bool ordered = n_cpt >= 0;
+  const size_t width = ordered ? n_cpt + 1 : 1;
+  const int n = static_cast<int>(d.n_rows);
+  if (d.score.n < static_cast<size_t>(n))
+    d.score.alloc(n);
+  d.accum.alloc(static_cast<size_t>(n) * width);
+  d.accum.zero(d.stream);
+  for (int s = 0; s < n_samples; s++) {
+    d.stage_sample(w0s[s], ws + static_cast<size_t>(s) * dim_all, Vs + static_cast<size_t>(s) * dim_all * K, K);
+    d.predict(d.w.p, d.Vt.p, K, d.w0.p, nullptr, d.score.p);
+    if (!n)
+      continue;
+    if (ordered) {
+      std::vector<Real> cp(n_cpt);
+      for (int c = 0; c < n_cpt; c++)
+        cp[c] = static_cast<Real>(cutpoints[static_cast<size_t>(s) * n_cpt + c]);
+      d.cutp.upload(cp, d.stream);
+      MYFM_CUDA(cudaStreamSynchronize(d.stream));
+      k_accumulate_oprobit<Real><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.cutp.p, n_cpt, d.accum.p);
+    } else if (task == MYFM_TASK_CLASSIFICATION) {
+      k_accumulate<Real, 1><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.accum.p);
+    } else if (task == MYFM_TASK_REGRESSION) {
+      k_accumulate<Real, 0><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.accum.p);
+    } // ORDERED through Predictor::predict leaves zeros (predictor.hpp:136-143)
+    d.count();
+  }
+  if (n) {
+    k_scale<Real><<<ceil_div(static_cast<int64_t>(n) * width, 256), 256, 0, d.stream>>>(
+        static_cast<int64_t>(n) * width, d.accum.p, static_cast<Real>(n_samples));
+    d.count();
+  }
+  std::vector<Real> h(static_cast<size_t>(n) * width);
+  d.accum.download(h.data(), h.size(), d.stream);
+  MYFM_CUDA(cudaStreamSynchronize(d.stream));
+  for (size_t i = 0; i < h.size(); i++)
+    out[i] = h[i];
+}
+
+} // namespace myfm
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace myfm;
+
+struct myfm_trainer {
+  std::unique_ptr<TrainerBase> impl;
+};
+struct myfm_dataset {
+  std::unique_ptr<DatasetBase> impl;
+};
+
+#define MYFM_API_BEGIN try {
+#define MYFM_API_END                                                                               \
+  return MYFM_OK;                                                                                  \
+  }                                                                                                \
+  catch (const std::invalid_argument &ex) {                                                        \
+    g_last_error = ex.what();                                                                      \
+    return MYFM_ERR_INVALID_ARGUMENT;                                                              \
+  }                                                                                                \
+  catch (const CudaError &ex) {                                                                    \
+    g_last_error = ex.what();                                                                      \
+    return MYFM_ERR_CUDA;                                                                          \
+  }                                                                                                \
+  catch (const std::exception &ex) {                                                               \
+    g_last_error = ex.what();                                                                      \
+    return MYFM_ERR_RUNTIME;                                                                       \
+  }
+
+static void require(const void *p, const char *what) {
+  if (!p)
+    throw std::invalid_argument(std::string(what) + " must not be NULL.");
+}
+
+extern "C" {
+
+const char *myfm_last_error(void) { return g_last_error.c_str(); }
+
+int myfm_device_count(int32_t *count) {
+  MYFM_API_BEGIN
+  require(count, "count");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  MYFM_API_END
+}
+
+int myfm_config_validate(const myfm_config_t *cfg, int32_t *n_groups) {
+  MYFM_API_BEGIN
+  require(cfg, "cfg");
+  Config c(*cfg);
+  if (n_groups)
+    *n_groups = c.n_groups;
+  MYFM_API_END
+}
+
+int myfm_trainer_create(myfm_trainer_t **out, const myfm_csr_t *X, int32_t n_relations,
+                        const myfm_relation_t *relations, const double *y, int64_t n_y,
+                        int32_t random_seed, const myfm_config_t *cfg, const myfm_engine_options_t *opt) {
+  MYFM_API_BEGIN
+  require(out, "out"), require(X, "X"), require(cfg, "cfg"), require(opt, "opt");
+  if (n_y > 0)
+    require(y, "y");
+  if (n_relations > 0)
+    require(relations, "relations");
+  auto holder = std::make_unique<myfm_trainer>();
+  if (opt->dtype == MYFM_DTYPE_F32)
+    holder->impl = std::make_unique<Trainer<float>>(*X, n_relations, relations, y, n_y, random_seed, *cfg, *opt);
+  else if (opt->dtype == MYFM_DTYPE_F64)
+    holder->impl = std::make_unique<Trainer<double>>(*X, n_relations, relations, y, n_y, random_seed, *cfg, *opt);
+  else
+    throw std::invalid_argument("unknown dtype.");
+  *out = holder.release();
+  MYFM_API_END
+}
+
+void myfm_trainer_destroy(myfm_trainer_t *t) { delete t; }
+
+int myfm_trainer_init_fm(myfm_trainer_t *t, int32_t rank, double init_std) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->init_fm(rank, init_std);
+  MYFM_API_END
+}
+int myfm_trainer_step(myfm_trainer_t *t, int32_t n_sweeps) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->step(n_sweeps);
+  MYFM_API_END
+}
+int myfm_trainer_sync(myfm_trainer_t *t) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->sync();
+  MYFM_API_END
+}
+int myfm_trainer_dims(const myfm_trainer_t *t, int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->dims(n_train, dim_all, rank, n_groups);
+  MYFM_API_END
+}
+int myfm_trainer_get_fm(myfm_trainer_t *t, double *w0, double *w, double *V) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->get_fm(w0, w, V);
+  MYFM_API_END
+}
+int myfm_trainer_get_cutpoints(myfm_trainer_t *t, int32_t g, double *out) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->get_cutpoints(g, out);
+  MYFM_API_END
+}
+int myfm_trainer_get_hyper(myfm_trainer_t *t, double *alpha, double *mu_w, double *lambda_w, double *mu_V,
+                           double *lambda_V) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->get_hyper(alpha, mu_w, lambda_w, mu_V, lambda_V);
+  MYFM_API_END
+}
+int myfm_trainer_get_e(myfm_trainer_t *t, double *e) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->get_e(e);
+  MYFM_API_END
+}
+int myfm_trainer_get_q(myfm_trainer_t *t, double *q) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->get_q(q);
+  MYFM_API_END
+}
+int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(count, "count");
+  *count = t->impl->mh_accept(g);
+  MYFM_API_END
+}
+int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(count, "count");
+  *count = t->impl->launch_count();
+  MYFM_API_END
+}
+int myfm_trainer_set_profiling(myfm_trainer_t *t, int32_t on) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->set_profiling(on != 0);
+  MYFM_API_END
+}
+int myfm_trainer_kernel_ms(myfm_trainer_t *t, int32_t family, double *ms, int64_t *launches) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(ms, "ms"), require(launches, "launches");
+  t->impl->kernel_ms(family, ms, launches);
+  MYFM_API_END
+}
+
+int myfm_dataset_create(myfm_dataset_t **out, const myfm_csr_t *X, int32_t n_relations,
+                        const myfm_relation_t *relations, int32_t dtype, int32_t device) {
+  MYFM_API_BEGIN
+  require(out, "out"), require(X, "X");
+  if (n_relations > 0)
+    require(relations, "relations");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device)
+    throw CudaError("no usable CUDA device: the myfm_b200 engine has no CPU fallback.");
+  MYFM_CUDA(cudaSetDevice(device));
+  auto holder = std::make_unique<myfm_dataset>();
+  auto make = [&](auto tag) {
+    using Real = decltype(tag);
+    auto d = std::make_unique<Dataset<Real>>();
+    d->dtype = dtype, d->device = device;
+    cudaStream_t s;
+    MYFM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    d->own_stream = true;
+    d->stream = s;
+    d->build(host_from_api<Real>(*X, "X"), n_relations, relations, s);
+    holder->impl = std::move(d);
+  };
+  if (dtype == MYFM_DTYPE_F32)
+    make(float{});
+  else if (dtype == MYFM_DTYPE_F64)
+    make(double{});
+  else
+    throw std::invalid_argument("unknown dtype.");
+  *out = holder.release();
+  MYFM_API_END
+}
+void myfm_dataset_destroy(myfm_dataset_t *d) { delete d; }
+
+int myfm_predict_score(const myfm_dataset_t *d, double w0, const double *w, const double *V, int64_t dim_all,
+                       int32_t rank, double *out) {
+  MYFM_API_BEGIN
+  require(d, "dataset");
+  if (d->impl->dtype == MYFM_DTYPE_F32)
+    dataset_predict_score(*static_cast<Dataset<float> *>(d->impl.get()), w0, w, V, dim_all, rank, out);
+  else
+    dataset_predict_score(*static_cast<Dataset<double> *>(d->impl.get()), w0, w, V, dim_all, rank, out);
+  MYFM_API_END
+}
+
+int myfm_predict_mean(const myfm_dataset_t *d, int32_t task_type, int32_t n_samples, const double *w0s,
+                      const double *ws, const double *Vs, int64_t dim_all, int32_t rank, double *out) {
+  MYFM_API_BEGIN
+  require(d, "dataset");
+  if (d->impl->dtype == MYFM_DTYPE_F32)
+    dataset_predict_mean(*static_cast<Dataset<float> *>(d->impl.get()), task_type, n_samples, w0s, ws, Vs, nullptr,
+                         -1, dim_all, rank, out);
+  else
+    dataset_predict_mean(*static_cast<Dataset<double> *>(d->impl.get()), task_type, n_samples, w0s, ws, Vs, nullptr,
+                         -1, dim_all, rank, out);
+  MYFM_API_END
+}
+
+int myfm_predict_oprobit_mean(const myfm_dataset_t *d, int32_t n_samples, const double *w0s, const double *ws,
+                              const double *Vs, const double *cutpoints, int32_t n_cpt, int64_t dim_all,
+                              int32_t rank, double *out) {
+  MYFM_API_BEGIN
+  require(d, "dataset");
+  if (n_cpt < 0)
+    throw std::invalid_argument("n_cpt must be non-negative.");
+  if (d->impl->dtype == MYFM_DTYPE_F32)
+    dataset_predict_mean(*static_cast<Dataset<float> *>(d->impl.get()), MYFM_TASK_ORDERED, n_samples, w0s, ws, Vs,
+                         cutpoints, n_cpt, dim_all, rank, out);
+  else
+    dataset_predict_mean(*static_cast<Dataset<double> *>(d->impl.get()), MYFM_TASK_ORDERED, n_samples, w0s, ws, Vs,
+                         cutpoints, n_cpt, dim_all, rank, out);
+  MYFM_API_END
+}
+
+int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, double *out) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(d, "dataset");
+  t->impl->predict_score(d->impl.get(), out);
+  MYFM_API_END
+}
+
+// kinds[i]: 0 = fresh standard normal (FMTrainer.hpp:122-125), 1 = fresh Gamma(shapes[i], 1)
+// (FMTrainer.hpp:143,165); the first n_skip draws of one PERSISTENT normal_distribution are
+// consumed beforehand (FM.hpp:34-45).
+int myfm_rng_fill(int32_t dtype, int32_t seed, int64_t n_skip_normals_persistent, const int32_t *kinds,
+                  const double *shapes, int64_t n, double *out) {
+  MYFM_API_BEGIN
+  auto run = [&](auto tag) {
+    using Real = decltype(tag);
+    MtStream<Real> s(seed);
+    {
+      std::vector<Real> sink(n_skip_normals_persistent + 1);
+      if (n_skip_normals_persistent > 0) {
+        Real w0;
+        s.init_weights(sink.data(), n_skip_normals_persistent - 1, sink.data(), 0, &w0, Real(1));
+      }
+    }
+    for (int64_t i = 0; i < n; i++)
+      out[i] = kinds[i] == 0 ? s.normal() : s.gamma(static_cast<Real>(shapes[i]));
+  };
+  if (dtype == MYFM_DTYPE_F32)
+    run(float{});
+  else
+    run(double{});
+  MYFM_API_END
+}
+
+int myfm_level_schedule(const myfm_csr_t *X, int32_t *level, int32_t *n_levels) {
+  MYFM_API_BEGIN
+  require(X, "X"), require(n_levels, "n_levels");
+  HostCs<float> Xt = host_transpose(host_from_api<float>(*X, "X"));
+  int nl = 0;
+  std::vector<int> lv = compute_levels(Xt, &nl);
+  for (size_t j = 0; j < lv.size(); j++)
+    level[j] = lv[j];
+  *n_levels = nl;
+  MYFM_API_END
+}
+
+} // extern "C"

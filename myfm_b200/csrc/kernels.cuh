@@ -1,0 +1,648 @@
+// sm_100a kernels of the Gibbs sweep.  All of them are HBM/L2-bound gather/scatter work: there is
+// no dense contraction, so no tensor cores.  Templated on Real (float =
+// reference's bind_float.cpp instantiation, double = what the reference ships).
+//
+// Arithmetic is written in the reference's operation order and the file is compiled with
+// -fmad=false, so every element-wise result is bit-identical to the CPU path; the only
+// differences are the order of the per-column / per-vector sums (warp trees instead of a serial
+// accumulator) and log/exp in the variates.
+#pragma once
+
+#include "common.cuh"
+
+namespace myfm {
+
+constexpr int MAX_REL = 8; // relation blocks per model
+
+template <typename Real> struct CsView { // CSR or CSC, device pointers
+  const int *ptr = nullptr;
+  const int *idx = nullptr;
+  const Real *val = nullptr;
+};
+
+// Per-block tables consumed by the forward pass: for block row s and factor r
+// q[s*K + r] = (X_B V_B[:,r])[s], qs[s*K + r] = (X_B^2 V_B[:,r]^2)[s], lin[s] = (X_B w_B)[s].
+template <typename Real> struct RelPredictView {
+  const int *map = nullptr; // [n_rows] -> block row
+  const Real *lin = nullptr;
+  const Real *q = nullptr;
+  const Real *qs = nullptr;
+};
+template <typename Real> struct RelPredictPack {
+  int n = 0;
+  RelPredictView<Real> r[MAX_REL];
+};
+
+// ----------------------------------------------------------------------------------------------
+// Row-parallel SpMV: out[i] = sum_p val[p] * x[idx[p]]      (q_init; FMTrainer.hpp:320,331)
+// SQUARED: out[i] = sum_p val[p]^2 * x[idx[p]]^2           (q_S;    FMTrainer.hpp:388-393)
+// LPR lanes cooperate on one row.
+// ----------------------------------------------------------------------------------------------
+template <typename Real, int LPR, bool SQUARED>
+__global__ void __launch_bounds__(256) k_spmv(int n_rows, CsView<Real> A, const Real *__restrict__ x,
+                                               Real *__restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sub = tid % LPR;
+  Real acc = 0;
+  if (row < n_rows) {
+    const int b = A.ptr[row], en = A.ptr[row + 1];
+    for (int p = b + sub; p < en; p += LPR) {
+      Real v = A.val[p], xv = x[A.idx[p]];
+      acc += SQUARED ? (v * v) * (xv * xv) : v * xv;
+    }
+  }
+  acc = subwarp_sum<Real, LPR>(acc);
+  if (row < n_rows && sub == 0)
+    out[row] = acc;
+}
+
+// Block tables for the forward pass, one launch per block: warp per block row, lanes over factors.
+// Vt is feature-major [dim_all x K]; `offset` is the block's first feature.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_block_tables(int n_block_rows, CsView<Real> B, const Real *__restrict__ w,
+                   const Real *__restrict__ Vt, int K, int offset, Real *__restrict__ lin,
+                   Real *__restrict__ q, Real *__restrict__ qs) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n_block_rows)
+    return;
+  const int b = B.ptr[s], en = B.ptr[s + 1];
+  Real l = 0;
+  for (int p = b + lane; p < en; p += 32)
+    l += B.val[p] * w[offset + B.idx[p]];
+  l = warp_sum(l);
+  if (lane == 0)
+    lin[s] = l;
+  for (int r = lane; r < K; r += 32) {
+    Real a = 0, a2 = 0;
+    for (int p = b; p < en; p++) {
+      Real x = B.val[p], v = Vt[static_cast<size_t>(offset + B.idx[p]) * K + r];
+      a += x * v;
+      a2 += (x * x) * (v * v);
+    }
+    q[static_cast<size_t>(s) * K + r] = a;
+    qs[static_cast<size_t>(s) * K + r] = a2;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Forward pass, all K factors fused in ONE pass over the CSR (FM.hpp:54-136 does 2K SpMVs):
+//   out[i] = w0 + X w + sum_b lin_b[map_b(i)] + 1/2 sum_r [ q_r^2 - s_r ]   ( - y[i] if y )
+// LPR lanes per row; lane `sub` owns factors sub, sub+LPR, ...
+// ----------------------------------------------------------------------------------------------
+template <typename Real, int LPR>
+__global__ void __launch_bounds__(256)
+    k_predict(int n_rows, CsView<Real> X, const Real *__restrict__ w, const Real *__restrict__ Vt,
+              int K, const Real *__restrict__ w0_ptr, RelPredictPack<Real> rels,
+              const Real *__restrict__ y, Real *__restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sub = tid % LPR;
+  Real lin = 0, acc = 0;
+  if (row < n_rows) {
+    const int b = X.ptr[row], en = X.ptr[row + 1];
+    for (int p = b + sub; p < en; p += LPR)
+      lin += X.val[p] * w[X.idx[p]];
+    int srow[MAX_REL];
+#pragma unroll
+    for (int k = 0; k < MAX_REL; k++)
+      if (k < rels.n) {
+        srow[k] = rels.r[k].map[row];
+        if (sub == 0)
+          lin += rels.r[k].lin[srow[k]];
+      }
+    const Real half = static_cast<Real>(0.5);
+    for (int r = sub; r < K; r += LPR) {
+      Real qr = 0, sr = 0;
+      for (int p = b; p < en; p++) {
+        Real x = X.val[p], v = Vt[static_cast<size_t>(X.idx[p]) * K + r];
+        qr += x * v;
+        sr += (x * x) * (v * v);
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_REL; k++)
+        if (k < rels.n) {
+          qr += rels.r[k].q[static_cast<size_t>(srow[k]) * K + r];
+          sr += rels.r[k].qs[static_cast<size_t>(srow[k]) * K + r];
+        }
+      acc += (qr * qr) * half;
+      acc -= sr * half;
+    }
+  }
+  lin = subwarp_sum<Real, LPR>(lin);
+  acc = subwarp_sum<Real, LPR>(acc);
+  if (row < n_rows && sub == 0) {
+    Real t = (*w0_ptr + lin) + acc;
+    out[row] = y ? t - y[row] : t;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Scalars of one sweep live in a small device array so that no step needs the host.
+// ----------------------------------------------------------------------------------------------
+template <typename Real> struct HyperView {
+  Real *alpha;    // [1]
+  Real *w0;       // [1]
+  Real *mu_w;     // [G]
+  Real *lambda_w; // [G]
+  Real *mu_V;     // [G x K] column-major (g + G*r), as in HyperParams.hpp
+  Real *lambda_V; // [G x K]
+};
+
+// Stage 1 of a deterministic grid reduction of f(e_i): block partials.
+// MODE 0: e^2 (update_alpha, FMTrainer.hpp:138)   MODE 1: (w0 - e) (update_w0, :223)
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(512)
+    k_reduce_e(int64_t n, const Real *__restrict__ e, const Real *__restrict__ w0_ptr,
+               Real *__restrict__ partial) {
+  __shared__ Real scratch[32];
+  Real acc = 0;
+  const Real w0 = MODE == 1 ? *w0_ptr : Real(0);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    Real v = e[i];
+    acc += MODE == 0 ? v * v : (w0 - v);
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0)
+    partial[blockIdx.x] = acc;
+}
+
+// Stage 2 (one block): alpha ~ Gamma((alpha_0+N)/2, 2/(beta_0+sum e^2)) from a standardised
+// Gamma variate (FMTrainer.hpp:140-144).
+template <typename Real>
+__global__ void k_finish_alpha(int n_partial, const Real *__restrict__ partial, Real beta_0,
+                               const Real *__restrict__ g_std, Real *alpha) {
+  __shared__ Real scratch[32];
+  Real acc = 0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x)
+    acc += partial[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) {
+    Real variance = (beta_0 + acc) / 2;
+    *alpha = *g_std * (1 / variance);
+  }
+}
+
+// Stage 2 of update_w0 (FMTrainer.hpp:223-228): draws w0 and leaves delta = w0_new - w0_old.
+template <typename Real>
+__global__ void k_finish_w0(int n_partial, const Real *__restrict__ partial, int n_train, Real reg_0,
+                            const Real *__restrict__ alpha_ptr, const Real *__restrict__ z,
+                            Real *w0, Real *delta) {
+  __shared__ Real scratch[32];
+  Real acc = 0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x)
+    acc += partial[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) {
+    Real alpha = *alpha_ptr;
+    Real lin = alpha * acc;
+    Real quad = alpha * n_train + reg_0;
+    Real w0_new = (lin / quad) + *z / sqrt(quad);
+    *delta = (w0_new - *w0);
+    *w0 = w0_new;
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_add_scalar(int64_t n, Real *__restrict__ e, const Real *__restrict__ delta) {
+  const Real d = *delta;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    e[i] += d;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Group hyper-parameters (FMTrainer.hpp:150-216).  One block per (group, vector); the vector is
+// w (n_vec == 1) or one factor column of V.  lambda first (with the old mu), then mu.
+//   lambda_g = Gamma((alpha_0+n_g)/2, 1) * 2/(beta_0 + sum (theta-mu_g)^2)
+//   mu_g     = lin/quad + z/sqrt(quad),  quad = lambda_g (gamma_0+n_g),
+//              lin = lambda_g (gamma_0 mu_0 + sum theta)
+// feat_ptr/feat_idx: features of each group, ascending.
+// ----------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_group_hyper(int G, const int *__restrict__ feat_ptr, const int *__restrict__ feat_idx,
+                  const Real *__restrict__ theta, int64_t theta_stride, Real *mu, Real *lambda,
+                  const Real *__restrict__ g_std, const Real *__restrict__ z, Real beta_0,
+                  Real gamma_0, Real mu_0) {
+  __shared__ Real scratch[32];
+  const int g = blockIdx.x % G, v = blockIdx.x / G;
+  const Real *th = theta + theta_stride * v;
+  const int b = feat_ptr[g], en = feat_ptr[g + 1];
+  const Real mean = mu[g + G * v];
+  Real dev2 = 0, sum = 0;
+  for (int p = b + threadIdx.x; p < en; p += blockDim.x) {
+    Real t = th[feat_idx[p]];
+    Real dev = t - mean;
+    dev2 += dev * dev;
+    sum += t;
+  }
+  dev2 = block_sum(dev2, scratch);
+  sum = block_sum(sum, scratch);
+  if (threadIdx.x == 0) {
+    const int n_g = en - b;
+    Real beta = beta_0 + dev2;
+    Real lam = g_std[g + G * v] * (2 / beta);
+    lambda[g + G * v] = lam;
+    Real square = lam * (gamma_0 + n_g);
+    Real linear = gamma_0 * mu_0 + sum;
+    linear *= lam;
+    mu[g + G * v] = (linear / square) + z[g + G * v] / sqrt(square);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Column sweeps over one dependency level of the main table.  `cols` lists the level's columns;
+// they are pairwise row-disjoint, so the concurrent read-modify-write of e / q below is the
+// reference's serial loop, bit for bit, in any interleaving.
+//
+// V (FMTrainer.hpp:343-376):  h = x (q - x v_old);  sq = sum h^2;  lin = sum -e h + sq v_old
+//   v_new = draw(alpha sq + lambda, alpha lin + lambda mu);  q += x d;  e += h d
+// w (FMTrainer.hpp:237-254):  e' = e - x w_old;  sq = lambda + alpha sum x^2;
+//   lin = sum (-alpha x) e' + lambda mu;  e = e' + x w_new
+// ----------------------------------------------------------------------------------------------
+template <typename Real> struct SweepArgs {
+  CsView<Real> Xt;     // CSC of the main table
+  const int *cols;     // columns of this launch
+  int n_cols;
+  Real *e;
+  Real *q;             // unused for w
+  Real *theta;         // w, or column r of V (column-major)
+  Real *theta_t;       // feature-major mirror: theta_t[j * t_stride], or nullptr
+  int64_t t_stride;
+  const Real *z;       // standardised normals indexed by feature
+  const int *group;    // group of every feature
+  const Real *alpha;
+  const Real *lambda;  // [G] of this vector
+  const Real *mu;      // [G]
+};
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void column_pass1(const CsView<Real> &Xt, int p, Real theta_old,
+                                             const Real *e, const Real *q, Real alpha, Real &sq,
+                                             Real &lin) {
+  const int i = Xt.idx[p];
+  const Real x = Xt.val[p];
+  if (IS_V) {
+    Real h = x * (q[i] - x * theta_old);
+    sq += h * h;
+    lin += (-e[i]) * h;
+  } else {
+    Real e1 = e[i] - x * theta_old;
+    sq += x * x;
+    lin += ((-alpha) * x) * e1;
+  }
+}
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void column_pass2(const CsView<Real> &Xt, int p, Real theta_old,
+                                             Real theta_new, Real *e, Real *q) {
+  const int i = Xt.idx[p];
+  const Real x = Xt.val[p];
+  if (IS_V) {
+    Real qi = q[i];
+    Real h = x * (qi - x * theta_old);
+    q[i] = qi + x * (theta_new - theta_old);
+    e[i] += h * (theta_new - theta_old);
+  } else {
+    Real e1 = e[i] - x * theta_old;
+    e[i] = e1 + x * theta_new;
+  }
+}
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ Real column_draw(Real sq, Real lin, Real theta_old, Real alpha, Real lam,
+                                            Real mu, Real z) {
+  if (IS_V) {
+    lin += sq * theta_old;
+    sq *= alpha;
+    lin *= alpha;
+    sq += lam;
+    lin += lam * mu;
+  } else {
+    sq = lam + alpha * sq;
+    lin = lin + lam * mu;
+  }
+  return (lin / sq) + z / sqrt(sq);
+}
+
+// One warp per column (short columns).
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(256) k_sweep_warp(SweepArgs<Real> a) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= a.n_cols)
+    return;
+  const int j = a.cols[c];
+  const int b = a.Xt.ptr[j], en = a.Xt.ptr[j + 1];
+  const Real theta_old = a.theta[j];
+  const Real alpha = *a.alpha;
+  Real sq = 0, lin = 0;
+  for (int p = b + lane; p < en; p += 32)
+    column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
+  sq = warp_sum(sq);
+  lin = warp_sum(lin);
+  const int g = a.group[j];
+  const Real theta_new =
+      column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+  if (lane == 0) {
+    a.theta[j] = theta_new;
+    if (a.theta_t)
+      a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+  }
+  for (int p = b + lane; p < en; p += 32)
+    column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
+}
+
+// One thread block per column (long columns).
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(512) k_sweep_block(SweepArgs<Real> a) {
+  __shared__ Real scratch[32];
+  const int j = a.cols[blockIdx.x];
+  const int b = a.Xt.ptr[j], en = a.Xt.ptr[j + 1];
+  const Real theta_old = a.theta[j];
+  const Real alpha = *a.alpha;
+  Real sq = 0, lin = 0;
+  for (int p = b + threadIdx.x; p < en; p += blockDim.x)
+    column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
+  sq = block_sum(sq, scratch);
+  lin = block_sum(lin, scratch);
+  const int g = a.group[j];
+  const Real theta_new =
+      column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+  if (threadIdx.x == 0) {
+    a.theta[j] = theta_new;
+    if (a.theta_t)
+      a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+  }
+  for (int p = b + threadIdx.x; p < en; p += blockDim.x)
+    column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Relation blocks (FMTrainer.hpp:256-313 for w, :378-482 for V).  Rows are pre-grouped by block
+// row: seg_ptr[s]..seg_ptr[s+1] indexes `seg_rows` (ascending training row), so every block-row
+// aggregate is an order-deterministic segment sum, no atomics.
+// ----------------------------------------------------------------------------------------------
+template <typename Real> struct RelCache {
+  const Real *card; // [S]
+  Real *q, *q_S, *c, *c_S, *e, *e_q;
+};
+
+// out[i] += blk[map[i]]   (FMTrainer.hpp:309, :336)
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_rel_add_rows(int n, const int *__restrict__ map, const Real *__restrict__ blk,
+                   Real *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] += blk[map[i]];
+}
+
+// w part, FMTrainer.hpp:268-275: E[s] = sum e_i ; e_i -= qB[s].  Warp per block row.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_rel_gather_w(int S, const int *__restrict__ seg_ptr, const int *__restrict__ seg_rows,
+                   RelCache<Real> cache, Real *__restrict__ e) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= S)
+    return;
+  const Real qb = cache.q[s];
+  Real acc = 0;
+  for (int k = seg_ptr[s] + lane; k < seg_ptr[s + 1]; k += 32) {
+    const int i = seg_rows[k];
+    Real ei = e[i];
+    acc += ei;
+    e[i] = ei - qb;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0)
+    cache.e[s] = acc;
+}
+
+// V part, FMTrainer.hpp:396-417.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_rel_gather_v(int S, const int *__restrict__ seg_ptr, const int *__restrict__ seg_rows,
+                   RelCache<Real> cache, Real *__restrict__ e, Real *__restrict__ q) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= S)
+    return;
+  const Real qb = cache.q[s], qs = cache.q_S[s];
+  Real c = 0, c_S = 0, es = 0, e_q = 0;
+  for (int k = seg_ptr[s] + lane; k < seg_ptr[s + 1]; k += 32) {
+    const int i = seg_rows[k];
+    Real ei = e[i];
+    Real temp = (q[i] - qb);
+    c += temp;
+    c_S += temp * temp;
+    es += ei;
+    e_q += ei * temp;
+    q[i] = temp;
+    // 0.5 is a double literal in the reference: this expression is evaluated in double
+    e[i] = static_cast<Real>(ei - (temp * qb + 0.5 * qb * qb - 0.5 * qs));
+  }
+  c = warp_sum(c), c_S = warp_sum(c_S), es = warp_sum(es), e_q = warp_sum(e_q);
+  if (lane == 0)
+    cache.c[s] = c, cache.c_S[s] = c_S, cache.e[s] = es, cache.e_q[s] = e_q;
+}
+
+// FMTrainer.hpp:473-480
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_rel_resync_v(int n, const int *__restrict__ map, RelCache<Real> cache, Real *__restrict__ e,
+                   Real *__restrict__ q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int s = map[i];
+  const Real qb = cache.q[s], qs = cache.q_S[s], qi = q[i];
+  e[i] = static_cast<Real>(e[i] + (qi * qb + 0.5 * qb * qb - 0.5 * qs));
+  q[i] = qi + qb;
+}
+
+// Sweep over the columns of one block, in dependency levels of the block rows.  The chain of
+// levels is inherently serial and each level is tiny, so ONE persistent thread block walks it with
+// block barriers instead of one launch per level.  Levels with several
+// columns go warp-per-column; a level with a single column uses the whole block.
+template <typename Real> struct RelSweepArgs {
+  CsView<Real> Bt;      // CSC of the block (X_B^T)
+  int n_levels;
+  const int *level_ptr; // [n_levels + 1] into level_cols
+  const int *level_cols;
+  RelCache<Real> cache;
+  Real *theta;          // w or V[:, r], already offset to the block's first feature
+  Real *theta_t;        // feature-major mirror (offset likewise) or nullptr
+  int64_t t_stride;
+  const Real *z;        // offset likewise
+  const int *group;     // offset likewise
+  const Real *alpha;
+  const Real *lambda;
+  const Real *mu;
+};
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void rel_pass1(const RelSweepArgs<Real> &a, int p, Real theta_old,
+                                          Real &sq, Real &lin) {
+  const int s = a.Bt.idx[p];
+  const Real x = a.Bt.val[p];
+  if (IS_V) {
+    Real h_B = (a.cache.q[s] - x * theta_old);
+    Real h2 = h_B * h_B * a.cache.card[s] + 2 * a.cache.c[s] * h_B + a.cache.c_S[s];
+    h2 = x * x * h2;
+    sq += h2;
+    lin += (-a.cache.e[s] * h_B - a.cache.e_q[s]) * x;
+  } else {
+    sq += (x * x) * a.cache.card[s];
+    lin += (-x) * a.cache.e[s];
+  }
+}
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void rel_pass2(const RelSweepArgs<Real> &a, int p, Real theta_old,
+                                          Real theta_new) {
+  const int s = a.Bt.idx[p];
+  const Real x = a.Bt.val[p];
+  const Real delta = theta_new - theta_old;
+  if (IS_V) {
+    Real h_B = a.cache.q[s] - x * theta_old;
+    a.cache.q[s] += delta * x;
+    a.cache.q_S[s] += delta * (theta_new + theta_old) * x * x;
+    a.cache.e[s] += x * delta * (h_B * a.cache.card[s] + a.cache.c[s]);
+    a.cache.e_q[s] += x * delta * (h_B * a.cache.c[s] + a.cache.c_S[s]);
+  } else {
+    a.cache.e[s] += (x * a.cache.card[s]) * delta;
+  }
+}
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ Real rel_draw(Real sq, Real lin, Real theta_old, Real alpha, Real lam,
+                                         Real mu, Real z) {
+  lin += sq * theta_old;
+  if (IS_V) {
+    sq *= alpha;
+    lin *= alpha;
+    sq += lam;
+    lin += lam * mu;
+  } else {
+    sq = lam + alpha * sq;
+    lin = alpha * lin + lam * mu;
+  }
+  return (lin / sq) + z / sqrt(sq);
+}
+
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(1024) k_rel_sweep(RelSweepArgs<Real> a) {
+  __shared__ Real scratch[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const Real alpha = *a.alpha;
+  for (int lv = 0; lv < a.n_levels; lv++) {
+    const int cb = a.level_ptr[lv], ce = a.level_ptr[lv + 1];
+    if (ce - cb == 1) { // the whole block works on the single column of this level
+      const int l = a.level_cols[cb];
+      const int b = a.Bt.ptr[l], en = a.Bt.ptr[l + 1];
+      const Real theta_old = a.theta[l];
+      Real sq = 0, lin = 0;
+      for (int p = b + threadIdx.x; p < en; p += blockDim.x)
+        rel_pass1<Real, IS_V>(a, p, theta_old, sq, lin);
+      sq = block_sum(sq, scratch);
+      lin = block_sum(lin, scratch);
+      const int g = a.group[l];
+      const Real theta_new =
+          rel_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[l]);
+      if (threadIdx.x == 0) {
+        a.theta[l] = theta_new;
+        if (a.theta_t)
+          a.theta_t[static_cast<int64_t>(l) * a.t_stride] = theta_new;
+      }
+      for (int p = b + threadIdx.x; p < en; p += blockDim.x)
+        rel_pass2<Real, IS_V>(a, p, theta_old, theta_new);
+    } else {
+      for (int ci = cb + wid; ci < ce; ci += nwarps) {
+        const int l = a.level_cols[ci];
+        const int b = a.Bt.ptr[l], en = a.Bt.ptr[l + 1];
+        const Real theta_old = a.theta[l];
+        Real sq = 0, lin = 0;
+        for (int p = b + lane; p < en; p += 32)
+          rel_pass1<Real, IS_V>(a, p, theta_old, sq, lin);
+        sq = warp_sum(sq);
+        lin = warp_sum(lin);
+        const int g = a.group[l];
+        const Real theta_new =
+            rel_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[l]);
+        if (lane == 0) {
+          a.theta[l] = theta_new;
+          if (a.theta_t)
+            a.theta_t[static_cast<int64_t>(l) * a.t_stride] = theta_new;
+        }
+        for (int p = b + lane; p < en; p += 32)
+          rel_pass2<Real, IS_V>(a, p, theta_old, theta_new);
+      }
+    }
+    __syncthreads(); // next level reads the caches this one wrote
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Small utilities
+// ----------------------------------------------------------------------------------------------
+// Vt[j*K + r] = V[j + D*r]
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_transpose_V(int64_t D, int K, const Real *__restrict__ V, Real *__restrict__ Vt) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t < D * K) {
+    const int64_t j = t / K;
+    const int r = static_cast<int>(t % K);
+    Vt[t] = V[j + D * r];
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_fill(int64_t n, Real *p, Real v) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    p[i] = v;
+}
+
+// out[i] (+)= link(score[i]);  LINK 0: identity, 1: Phi(score) = (erf(score*sqrt(.5))+1)/2
+// (predictor.hpp:136-143)
+template <typename Real, int LINK>
+__global__ void __launch_bounds__(256)
+    k_accumulate(int n, const Real *__restrict__ score, Real *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  Real s = score[i];
+  if (LINK == 1)
+    s = (erf(s * static_cast<Real>(0.70710678118654752440)) + static_cast<Real>(1)) /
+        static_cast<Real>(2);
+  out[i] += s;
+}
+
+// FM.hpp:137-162 accumulated over samples; out is [n x (n_cpt+1)] row-major
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_accumulate_oprobit(int n, const Real *__restrict__ score, const Real *__restrict__ cutpoints,
+                         int n_cpt, Real *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const Real s = score[i];
+  Real prev = 0;
+  for (int c = 0; c < n_cpt; c++) {
+    Real cdf = (1 + erf((cutpoints[c] - s) * static_cast<Real>(0.70710678118654752440))) / 2;
+    out[static_cast<size_t>(i) * (n_cpt + 1) + c] += cdf - prev;
+    prev = cdf;
+  }
+  out[static_cast<size_t>(i) * (n_cpt + 1) + n_cpt] += 1 - prev;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_scale(int64_t n, Real *p, Real inv) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    p[i] /= inv;
+}
+
+} // namespace myfm
