@@ -127,6 +127,9 @@ int myfm_trainer_init_fm(myfm_trainer_t *t, int32_t rank, double init_std);
  * mu_V, V, e).  Asynchronous for regression; returns once the work is enqueued. */
 int myfm_trainer_step(myfm_trainer_t *t, int32_t n_sweeps);
 int myfm_trainer_sync(myfm_trainer_t *t);
+/* n_sweeps x update_all bracketed by CUDA events on the trainer's stream (synchronises on both
+ * sides); writes the device-side milliseconds. */
+int myfm_trainer_timed_steps(myfm_trainer_t *t, int32_t n_sweeps, double *ms);
 
 /* Current state (synchronises).  w: [dim_all]; V: [dim_all x rank] row-major. */
 int myfm_trainer_dims(const myfm_trainer_t *t, int64_t *n_train, int64_t *dim_all, int32_t *rank,
@@ -140,6 +143,11 @@ int myfm_trainer_get_hyper(myfm_trainer_t *t, double *alpha, double *mu_w, doubl
 /* residual cache e_train and factor cache q_train of this shard (tests / diagnostics) */
 int myfm_trainer_get_e(myfm_trainer_t *t, double *e);
 int myfm_trainer_get_q(myfm_trainer_t *t, double *q);
+/* Overwrite parts of the chain state (any pointer may be NULL = keep): warm start from a stored
+ * sample, and the per-sweep "teacher-forced" parity tests.  Layouts as in the getters above. */
+int myfm_trainer_set_state(myfm_trainer_t *t, const double *w0, const double *w, const double *V,
+                           const double *alpha, const double *mu_w, const double *lambda_w,
+                           const double *mu_V, const double *lambda_V, const double *e);
 /* OprobitSampler::accept_count of cutpoint group g (FMTrainer.hpp:83-85) */
 int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count);
 /* number of kernels this trainer has launched so far (bench.py's gpu_launches) */

@@ -253,7 +253,7 @@ class _DeviceDataset:
         self.dtype = dtype
 
     def __del__(self) -> None:
-        if getattr(self, "_h", None) is not None:
+        if getattr(self, "_h", None) is not None and _lib is not None:  # None at interpreter exit
             _lib.lib().myfm_dataset_destroy(self._h)
             self._h = None
 
@@ -552,7 +552,7 @@ class _TrainerHandle:
         self.rank = -1
 
     def __del__(self) -> None:
-        if getattr(self, "_h", None) is not None:
+        if getattr(self, "_h", None) is not None and _lib is not None:
             _lib.lib().myfm_trainer_destroy(self._h)
             self._h = None
 
@@ -567,6 +567,12 @@ class _TrainerHandle:
 
     def sync(self) -> None:
         _lib.check(_lib.lib().myfm_trainer_sync(self._h))
+
+    def timed_steps(self, n: int) -> float:
+        """n sweeps bracketed by CUDA events on the trainer's stream; device milliseconds."""
+        ms = C.c_double()
+        _lib.check(_lib.lib().myfm_trainer_timed_steps(self._h, C.c_int32(int(n)), C.byref(ms)))
+        return float(ms.value)
 
     def get_fm(self) -> Tuple[float, np.ndarray, np.ndarray, List[np.ndarray]]:
         w0 = C.c_double()
@@ -600,6 +606,26 @@ class _TrainerHandle:
         q = np.empty(self.n_train, dtype=np.float64)
         _lib.check(_lib.lib().myfm_trainer_get_q(self._h, _lib.vptr(q)))
         return q
+
+    def set_state(self, w0=None, w=None, V=None, hyper: Optional["FMHyperParameters"] = None,
+                  e=None) -> None:
+        """Overwrite parts of the chain state (warm start / teacher-forced parity tests)."""
+        keep = []
+
+        def arr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return _lib.vptr(a)
+
+        alpha = arr(np.asarray([hyper.alpha])) if hyper is not None else None
+        _lib.check(_lib.lib().myfm_trainer_set_state(
+            self._h, arr(np.asarray([w0])) if w0 is not None else None, arr(w), arr(V), alpha,
+            arr(hyper.mu_w) if hyper is not None else None,
+            arr(hyper.lambda_w) if hyper is not None else None,
+            arr(hyper.mu_V) if hyper is not None else None,
+            arr(hyper.lambda_V) if hyper is not None else None, arr(e)))
 
     def mh_accept(self, g: int) -> int:
         n = C.c_int64()

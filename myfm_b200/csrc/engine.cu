@@ -17,7 +17,7 @@ namespace myfm {
 namespace {
 thread_local std::string g_last_error;
 
-constexpr int LONG_COLUMN = 2048; // columns longer than this get a whole thread block
+constexpr int LONG_COLUMN = SEG_NNZ; // longer columns are cut into multi-block segments
 constexpr int REDUCE_BLOCKS = 592; // 4 x 148 SMs
 
 int pow2_ceil_clamped(double x, int lo, int hi) {
@@ -226,6 +226,7 @@ struct TrainerBase {
   virtual void init_fm(int rank, double init_std) = 0;
   virtual void step(int n) = 0;
   virtual void sync() = 0;
+  virtual double timed_steps(int n) = 0;
   virtual void dims(int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) const = 0;
   virtual void get_fm(double *w0, double *w, double *V) = 0;
   virtual void get_cutpoints(int g, double *out) = 0;
@@ -234,6 +235,9 @@ struct TrainerBase {
   virtual void get_e(double *e) = 0;
   virtual void get_q(double *q) = 0;
   virtual int64_t mh_accept(int g) = 0;
+  virtual void set_state(const double *w0, const double *w, const double *V, const double *alpha,
+                         const double *mu_w, const double *lambda_w, const double *mu_V,
+                         const double *lambda_V, const double *e) = 0;
   virtual int64_t launch_count() const = 0;
   virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
   virtual void set_profiling(bool on) = 0;
@@ -261,7 +265,8 @@ template <typename Real> struct Trainer : TrainerBase {
   Dataset<Real> data; // main table CSR + relation blocks (CSR, map, forward tables)
   DevCs<Real> Xt;     // CSC of the main table
   LevelPlan plan;
-  DevBuf<int> plan_cols;
+  DevBuf<int> plan_cols, seg_col, seg_lo, seg_hi, seg_slot, slot_ptr;
+  DevBuf<Real> seg_partial, seg_theta_old;
   std::vector<DevRelationTrain<Real>> rel_train;
 
   int64_t N = 0, D = 0, D_all = 0;
@@ -320,8 +325,15 @@ template <typename Real> struct Trainer : TrainerBase {
 
     HostCs<Real> Xth = host_transpose(Xh);
     Xt.upload(Xth, stream);
-    plan = make_level_plan(Xth, LONG_COLUMN);
+    plan = make_level_plan(Xth, LONG_COLUMN, SEG_NNZ);
     plan_cols.upload(plan.cols, stream);
+    seg_col.upload(plan.seg_col, stream);
+    seg_lo.upload(plan.seg_lo, stream);
+    seg_hi.upload(plan.seg_hi, stream);
+    seg_slot.upload(plan.seg_slot, stream);
+    slot_ptr.upload(plan.slot_ptr, stream);
+    seg_partial.alloc(2 * static_cast<size_t>(plan.max_segs));
+    seg_theta_old.alloc(plan.max_slots);
 
     rel_train.resize(n_rel);
     for (int b = 0; b < n_rel; b++) {
@@ -492,10 +504,14 @@ template <typename Real> struct Trainer : TrainerBase {
       const int base = plan.level_ptr[lv], n = plan.level_ptr[lv + 1] - base;
       const int n_long = plan.n_long[lv], n_short = n - n_long;
       TimedSpan span(timer, stream, 0);
-      if (n_long) {
-        a.cols = plan_cols.p + base, a.n_cols = n_long;
-        k_sweep_block<Real, IS_V><<<n_long, 512, 0, stream>>>(a);
-        launched();
+      if (n_long) { // segmented two-phase path: no column can serialise the level
+        const int sb = plan.seg_level_ptr[lv], n_seg = plan.seg_level_ptr[lv + 1] - sb;
+        SegPlanView sp{seg_col.p + sb, seg_lo.p + sb, seg_hi.p + sb, seg_slot.p + sb,
+                       slot_ptr.p + plan.slot_level_ptr[lv]};
+        a.cols = nullptr, a.n_cols = 0;
+        k_seg_stats<Real, IS_V><<<n_seg, SEG_THREADS, 0, stream>>>(a, sp, seg_partial.p, seg_theta_old.p);
+        k_seg_update<Real, IS_V><<<n_seg, SEG_THREADS, 0, stream>>>(a, sp, seg_partial.p, seg_theta_old.p);
+        launched(2);
       }
       if (n_short) {
         a.cols = plan_cols.p + base + n_long, a.n_cols = n_short;
@@ -707,6 +723,23 @@ template <typename Real> struct Trainer : TrainerBase {
     if (timer.enabled)
       timer.collect();
   }
+  double timed_steps(int n) override {
+    require_fm();
+    MYFM_CUDA(cudaSetDevice(device));
+    cudaEvent_t a, b;
+    MYFM_CUDA(cudaEventCreate(&a));
+    MYFM_CUDA(cudaEventCreate(&b));
+    sync();
+    MYFM_CUDA(cudaEventRecord(a, stream));
+    for (int i = 0; i < n; i++)
+      sweep();
+    MYFM_CUDA(cudaEventRecord(b, stream));
+    sync();
+    float ms = 0;
+    MYFM_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    return ms;
+  }
   void dims(int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) const override {
     *n_train = N, *dim_all = D_all, *rank = K, *n_groups = G;
   }
@@ -754,6 +787,56 @@ template <typename Real> struct Trainer : TrainerBase {
       out[i] = h[i];
   }
   int64_t mh_accept(int) override { return 0; }
+
+  // Overwrites parts of the chain state (NULL = keep).  Layouts as in the getters.
+  void set_state(const double *w0_in, const double *w_in, const double *V_in, const double *alpha_in,
+                 const double *mu_w_in, const double *lambda_w_in, const double *mu_V_in,
+                 const double *lambda_V_in, const double *e_in) override {
+    require_fm();
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    std::vector<Real> hh = fetch(hyper.p, hyper_size());
+    if (alpha_in)
+      hh[0] = static_cast<Real>(*alpha_in);
+    if (w0_in)
+      hh[1] = static_cast<Real>(*w0_in);
+    for (int g = 0; g < G; g++) {
+      if (mu_w_in)
+        hh[2 + g] = static_cast<Real>(mu_w_in[g]);
+      if (lambda_w_in)
+        hh[2 + G + g] = static_cast<Real>(lambda_w_in[g]);
+      for (int r = 0; r < K; r++) {
+        if (mu_V_in)
+          hh[2 + 2 * G + g + static_cast<size_t>(G) * r] = static_cast<Real>(mu_V_in[static_cast<size_t>(g) * K + r]);
+        if (lambda_V_in)
+          hh[2 + 2 * G + static_cast<size_t>(G) * K + g + static_cast<size_t>(G) * r] =
+              static_cast<Real>(lambda_V_in[static_cast<size_t>(g) * K + r]);
+      }
+    }
+    hyper.upload(hh, stream);
+    std::vector<Real> tmp;
+    if (w_in) {
+      tmp.assign(w_in, w_in + D_all);
+      w.upload(tmp, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (V_in) {
+      std::vector<Real> vt(static_cast<size_t>(D_all) * K), vc(vt.size());
+      for (int64_t j = 0; j < D_all; j++)
+        for (int r = 0; r < K; r++) {
+          Real v = static_cast<Real>(V_in[static_cast<size_t>(j) * K + r]);
+          vt[static_cast<size_t>(j) * K + r] = v;
+          vc[j + static_cast<size_t>(D_all) * r] = v;
+        }
+      Vt.upload(vt, stream);
+      V.upload(vc, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (e_in) {
+      tmp.assign(e_in, e_in + N);
+      e.upload(tmp, stream);
+    }
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
   int64_t launch_count() const override { return launches; }
   void kernel_ms(int family, double *ms, int64_t *n) override {
     sync();
@@ -951,6 +1034,12 @@ int myfm_trainer_sync(myfm_trainer_t *t) {
   t->impl->sync();
   MYFM_API_END
 }
+int myfm_trainer_timed_steps(myfm_trainer_t *t, int32_t n_sweeps, double *ms) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(ms, "ms");
+  *ms = t->impl->timed_steps(n_sweeps);
+  MYFM_API_END
+}
 int myfm_trainer_dims(const myfm_trainer_t *t, int64_t *n_train, int64_t *dim_all, int32_t *rank, int32_t *n_groups) {
   MYFM_API_BEGIN
   require(t, "trainer");
@@ -992,6 +1081,14 @@ int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count) {
   MYFM_API_BEGIN
   require(t, "trainer"), require(count, "count");
   *count = t->impl->mh_accept(g);
+  MYFM_API_END
+}
+int myfm_trainer_set_state(myfm_trainer_t *t, const double *w0, const double *w, const double *V,
+                           const double *alpha, const double *mu_w, const double *lambda_w,
+                           const double *mu_V, const double *lambda_V, const double *e) {
+  MYFM_API_BEGIN
+  require(t, "trainer");
+  t->impl->set_state(w0, w, V, alpha, mu_w, lambda_w, mu_V, lambda_V, e);
   MYFM_API_END
 }
 int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count) {

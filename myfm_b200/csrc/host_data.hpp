@@ -120,10 +120,16 @@ struct LevelPlan {
   std::vector<int> level_ptr;  // [n_levels + 1] into cols
   std::vector<int> n_long;     // [n_levels]
   std::vector<int> cols;
+  // long columns cut into segments of at most seg_nnz entries (k_seg_stats / k_seg_update)
+  std::vector<int> seg_level_ptr;  // [n_levels + 1] into seg_*
+  std::vector<int> seg_col, seg_lo, seg_hi, seg_slot;
+  std::vector<int> slot_level_ptr; // [n_levels + 1] into slot_ptr (one extra entry per level)
+  std::vector<int> slot_ptr;       // per level: [n_long + 1] segment offsets RELATIVE to the level
+  int max_slots = 0, max_segs = 0;
 };
 
 template <typename Real>
-LevelPlan make_level_plan(const HostCs<Real> &csc, int long_threshold) {
+LevelPlan make_level_plan(const HostCs<Real> &csc, int long_threshold, int seg_nnz = 1024) {
   LevelPlan plan;
   std::vector<int> level = compute_levels(csc, &plan.n_levels);
   plan.level_ptr.assign(plan.n_levels + 1, 0);
@@ -142,6 +148,27 @@ LevelPlan make_level_plan(const HostCs<Real> &csc, int long_threshold) {
     std::stable_sort(b, e, [&](int x, int y) { return len(x) > len(y); });
     plan.n_long[l] = static_cast<int>(
         std::find_if(b, e, [&](int j) { return len(j) <= long_threshold; }) - b);
+  }
+  plan.seg_level_ptr.assign(plan.n_levels + 1, 0);
+  plan.slot_level_ptr.assign(plan.n_levels + 1, 0);
+  for (int l = 0; l < plan.n_levels; l++) {
+    int segs_in_level = 0;
+    for (int k = 0; k < plan.n_long[l]; k++) {
+      const int j = plan.cols[plan.level_ptr[l] + k];
+      plan.slot_ptr.push_back(segs_in_level);
+      for (int lo = csc.ptr[j]; lo < csc.ptr[j + 1]; lo += seg_nnz) {
+        plan.seg_col.push_back(j);
+        plan.seg_lo.push_back(lo);
+        plan.seg_hi.push_back(std::min(lo + seg_nnz, csc.ptr[j + 1]));
+        plan.seg_slot.push_back(k);
+        segs_in_level++;
+      }
+    }
+    plan.slot_ptr.push_back(segs_in_level);
+    plan.seg_level_ptr[l + 1] = plan.seg_level_ptr[l] + segs_in_level;
+    plan.slot_level_ptr[l + 1] = static_cast<int>(plan.slot_ptr.size());
+    plan.max_slots = std::max(plan.max_slots, plan.n_long[l]);
+    plan.max_segs = std::max(plan.max_segs, segs_in_level);
   }
   return plan;
 }

@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256) k_sweep_warp(SweepArgs<Real> a) {
   const Real theta_old = a.theta[j];
   const Real alpha = *a.alpha;
   Real sq = 0, lin = 0;
+#pragma unroll 4
   for (int p = b + lane; p < en; p += 32)
     column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
   sq = warp_sum(sq);
@@ -350,33 +351,93 @@ __global__ void __launch_bounds__(256) k_sweep_warp(SweepArgs<Real> a) {
     if (a.theta_t)
       a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
   }
+#pragma unroll 4
   for (int p = b + lane; p < en; p += 32)
     column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
 }
 
-// One thread block per column (long columns).
+// Long columns are cut into segments of SEG_NNZ entries, one thread block each, so that a heavy
+// tail (one movie rated by 3 % of all rows) cannot serialise a level on one SM:
+//   k_seg_stats : per-segment partial (sum h^2, sum -e h)            -> partial[seg]
+//   k_seg_update: every segment of a column sums that column's partials in segment order
+//                 (deterministic, identical in every block), draws, and updates its own rows.
+// The same stats -> (reduce) -> update split is what row-sharded multi-GPU training needs.
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_PER_THREAD = 4;
+constexpr int SEG_NNZ = SEG_THREADS * SEG_PER_THREAD;
+
+struct SegPlanView {
+  const int *seg_col;   // [n_seg] column of the segment
+  const int *seg_lo;    // [n_seg] first entry (absolute position in the CSC arrays)
+  const int *seg_hi;    // [n_seg] one past the last entry
+  const int *seg_slot;  // [n_seg] index of the column among the launch's long columns
+  const int *slot_ptr;  // [n_slots + 1] segments of each long column
+};
+
 template <typename Real, bool IS_V>
-__global__ void __launch_bounds__(512) k_sweep_block(SweepArgs<Real> a) {
+__global__ void __launch_bounds__(SEG_THREADS)
+    k_seg_stats(SweepArgs<Real> a, SegPlanView sp, Real *__restrict__ partial,
+                Real *__restrict__ theta_old_buf) {
   __shared__ Real scratch[32];
-  const int j = a.cols[blockIdx.x];
-  const int b = a.Xt.ptr[j], en = a.Xt.ptr[j + 1];
+  const int s = blockIdx.x;
+  const int j = sp.seg_col[s];
+  const int lo = sp.seg_lo[s], hi = sp.seg_hi[s];
   const Real theta_old = a.theta[j];
   const Real alpha = *a.alpha;
   Real sq = 0, lin = 0;
-  for (int p = b + threadIdx.x; p < en; p += blockDim.x)
-    column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
+#pragma unroll
+  for (int k = 0; k < SEG_PER_THREAD; k++) {
+    const int p = lo + threadIdx.x + k * SEG_THREADS;
+    if (p < hi)
+      column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
+  }
   sq = block_sum(sq, scratch);
   lin = block_sum(lin, scratch);
-  const int g = a.group[j];
-  const Real theta_new =
-      column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
   if (threadIdx.x == 0) {
+    partial[2 * s] = sq;
+    partial[2 * s + 1] = lin;
+    if (sp.slot_ptr[sp.seg_slot[s]] == s) // first segment snapshots the old value for the update
+      theta_old_buf[sp.seg_slot[s]] = theta_old;
+  }
+}
+
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(SEG_THREADS)
+    k_seg_update(SweepArgs<Real> a, SegPlanView sp, const Real *__restrict__ partial,
+                 const Real *__restrict__ theta_old_buf) {
+  __shared__ Real bcast[2];
+  const int s = blockIdx.x;
+  const int j = sp.seg_col[s];
+  const int slot = sp.seg_slot[s];
+  const int first = sp.slot_ptr[slot], last = sp.slot_ptr[slot + 1];
+  if (threadIdx.x < 32) {
+    Real sq = 0, lin = 0;
+    for (int i = first + threadIdx.x; i < last; i += 32) {
+      sq += partial[2 * i];
+      lin += partial[2 * i + 1];
+    }
+    sq = warp_sum(sq);
+    lin = warp_sum(lin);
+    if (threadIdx.x == 0)
+      bcast[0] = sq, bcast[1] = lin;
+  }
+  __syncthreads();
+  const Real theta_old = theta_old_buf[slot];
+  const int g = a.group[j];
+  const Real theta_new = column_draw<Real, IS_V>(bcast[0], bcast[1], theta_old, *a.alpha,
+                                                 a.lambda[g], a.mu[g], a.z[j]);
+  if (s == first && threadIdx.x == 0) {
     a.theta[j] = theta_new;
     if (a.theta_t)
       a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
   }
-  for (int p = b + threadIdx.x; p < en; p += blockDim.x)
-    column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
+  const int lo = sp.seg_lo[s], hi = sp.seg_hi[s];
+#pragma unroll
+  for (int k = 0; k < SEG_PER_THREAD; k++) {
+    const int p = lo + threadIdx.x + k * SEG_THREADS;
+    if (p < hi)
+      column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -1,0 +1,121 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/myfm_b200.h declares;
+host-only entry points (config validation, level schedule, RNG stream) work on the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from helpers import middle_data, movielens_like, toy_matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "myfm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(myfm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from myfm_b200 import _lib
+
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/myfm_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_device_probe_never_fails():
+    from myfm_b200 import _lib
+
+    assert _lib.device_count() >= 0
+
+
+def test_no_cpu_fallback_when_no_device():
+    import myfm_b200
+    from myfm_b200 import _lib
+
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    X, y = toy_matrix()
+    with pytest.raises(_lib.CudaEngineError, match="no CPU fallback"):
+        myfm_b200.MyFMRegressor(2).fit(X, y, n_iter=2)
+    from myfm_b200._myfm import FM
+
+    with pytest.raises(_lib.CudaEngineError):
+        FM(0.0, np.zeros(9), np.zeros((9, 2))).predict_score(X, [])
+
+
+def level_schedule(X):
+    from myfm_b200 import _lib
+
+    h = _lib.CsrHolder(X)
+    level = np.empty(X.shape[1], dtype=np.int32)
+    n = C.c_int32()
+    _lib.check(_lib.lib().myfm_level_schedule(C.byref(h.struct), _lib.vptr(level), C.byref(n)))
+    return level, n.value
+
+
+def test_level_schedule_one_hot_fields():
+    X, _, shapes = movielens_like(2000, 50, 20, 2, seed=0)
+    level, n = level_schedule(X)
+    assert n == 2
+    assert np.all(level[: shapes[0]] == 0) and np.all(level[shapes[0]:] == 1)
+
+
+def test_level_schedule_respects_serial_order():
+    """Columns of one level never share a row, and a column's level exceeds that of every earlier
+    column it shares a row with (so level order == the reference's index order)."""
+    rng = np.random.default_rng(0)
+    X = sps.random(60, 25, 0.15, format="csr", random_state=1)
+    level, n = level_schedule(X)
+    dense = X.toarray() != 0
+    for j in range(X.shape[1]):
+        for i in range(j):
+            if np.any(dense[:, i] & dense[:, j]):
+                assert level[i] < level[j]
+    for lv in range(n):
+        cols = np.where(level == lv)[0]
+        assert np.all(dense[:, cols].sum(axis=1) <= 1)
+    Xd, _ = toy_matrix()
+    level, n = level_schedule(Xd)
+    assert n == 3 and level[0] == 0 and set(level[1:5]) == {1} and set(level[5:]) == {2}
+    Xm, _ = middle_data(50)
+    assert level_schedule(Xm)[1] == 3
+
+
+def rng_fill(dtype, seed, n_skip, kinds, shapes):
+    from myfm_b200 import _lib
+
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+    shapes = np.ascontiguousarray(shapes, dtype=np.float64)
+    out = np.empty(kinds.shape[0])
+    _lib.check(_lib.lib().myfm_rng_fill(C.c_int32(_lib.DTYPES[dtype]), C.c_int32(seed), C.c_int64(n_skip),
+                                        _lib.vptr(kinds), _lib.vptr(shapes), C.c_int64(kinds.shape[0]),
+                                        _lib.vptr(out)))
+    return out
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_engine_rng_stream_is_the_libstdcxx_stream(oracle, dtype):
+    """A fresh normal_distribution per draw drops the second polar variate, so the engine's k-th
+    fresh normal is element 2k of one persistent distribution on the same mt19937."""
+    persistent = oracle.kat_normal(dtype, 42, 64)
+    fresh = rng_fill(dtype, 42, 0, [0] * 32, [0] * 32)
+    np.testing.assert_array_equal(fresh, persistent[0::2])
+    # after an even number of persistent draws the stream is aligned the same way
+    fresh_after = rng_fill(dtype, 42, 10, [0] * 8, [0] * 8)
+    np.testing.assert_array_equal(fresh_after, persistent[10:26:2])
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_engine_gamma_is_standardised(dtype):
+    g = rng_fill(dtype, 7, 0, [1] * 2000, [2.5] * 2000)
+    assert abs(g.mean() - 2.5) < 0.15 and abs(g.var() - 2.5) < 0.5
+    big = rng_fill(dtype, 7, 0, [1] * 200, [5.0e6] * 200)
+    assert abs(big.mean() / 5.0e6 - 1) < 1e-3
