@@ -17,7 +17,6 @@ namespace myfm {
 namespace {
 thread_local std::string g_last_error;
 
-constexpr int LONG_COLUMN = SEG_NNZ; // longer columns are cut into multi-block segments
 constexpr int REDUCE_BLOCKS = 592; // 4 x 148 SMs
 
 int pow2_ceil_clamped(double x, int lo, int hi) {
@@ -113,7 +112,9 @@ template <typename Real> struct Dataset : DatasetBase {
   void count(int n = 1) { (launch_counter ? *launch_counter : own_counter) += n; }
 
   // Shape checks of util.hpp:147-165 / definitions.hpp:38-41, then upload.
-  void build(const HostCs<Real> &Xh, int n_rel, const myfm_relation_t *relations, cudaStream_t s) {
+  // `perm` (trainer only): device row i holds the caller's row perm[i]; Xh is already permuted.
+  void build(const HostCs<Real> &Xh, int n_rel, const myfm_relation_t *relations, cudaStream_t s,
+             const std::vector<int> *perm = nullptr) {
     stream = s;
     n_rows = Xh.n_major;
     dim_main = Xh.n_minor;
@@ -133,9 +134,10 @@ template <typename Real> struct Dataset : DatasetBase {
       HostCs<Real> Bh = host_from_api<Real>(r.block, "relation block");
       std::vector<int> map(r.mapper_size);
       for (int64_t i = 0; i < r.mapper_size; i++) {
-        if (r.original_to_block[i] < 0 || r.original_to_block[i] >= Bh.n_major)
+        const int64_t v = r.original_to_block[perm ? (*perm)[i] : i];
+        if (v < 0 || v >= Bh.n_major)
           throw std::runtime_error("index mapping points to non-existing row.");
-        map[i] = static_cast<int>(r.original_to_block[i]);
+        map[i] = static_cast<int>(v);
       }
       DevRelationData<Real> &d = rels[b];
       d.S = Bh.n_major, d.F = Bh.n_minor, d.offset = dim_all;
@@ -159,7 +161,7 @@ template <typename Real> struct Dataset : DatasetBase {
 
   // out = predict_score(X, rels) [- y]; FM.hpp:54-136 with all factors fused in one CSR pass.
   void predict(const Real *w_dev, const Real *Vt_dev, int K, const Real *w0_dev, const Real *y,
-               Real *out) {
+               Real *out, int out_stride = 1) {
     ensure_tables(K);
     RelPredictPack<Real> pack;
     pack.n = static_cast<int>(rels.size());
@@ -180,7 +182,7 @@ template <typename Real> struct Dataset : DatasetBase {
 #define MYFM_PREDICT(L)                                                                            \
   case L:                                                                                          \
     k_predict<Real, L><<<ceil_div(static_cast<int64_t>(n) * L, 256), 256, 0, stream>>>(            \
-        n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out);                                      \
+        n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out, out_stride);                          \
     break;
     switch (lpr) {
       MYFM_PREDICT(1)
@@ -262,17 +264,21 @@ template <typename Real> struct Trainer : TrainerBase {
   int64_t launches = 0;
   KernelTimer timer;
 
-  Dataset<Real> data; // main table CSR + relation blocks (CSR, map, forward tables)
-  DevCs<Real> Xt;     // CSC of the main table
-  LevelPlan plan;
-  DevBuf<int> plan_cols, seg_col, seg_lo, seg_hi, seg_slot, slot_ptr;
+  Dataset<Real> data; // main table CSR + relation blocks (CSR, map, forward tables), device row order
+  DevCs<Real> Xt;     // CSC of the main table (device row order)
+  SweepPlan plan;
+  std::vector<int> perm; // device row i holds the caller's row perm[i] (host_data.hpp)
+  DevBuf<int> perm_dev;
+  DevBuf<int> item_col, item_lo, item_hi, seg_first, seg_count;
   DevBuf<Real> seg_partial, seg_theta_old;
+  DevBuf<Real> dense_tmp; // [N] staging for boundary copies of e / q
   std::vector<DevRelationTrain<Real>> rel_train;
 
   int64_t N = 0, D = 0, D_all = 0;
   int K = -1, G = 0;
   std::vector<Real> y_host;
-  DevBuf<Real> y, e, q;
+  DevBuf<Real> y;
+  DevBuf<Real> eq_buf;         // interleaved {e_i, q_i}, [2 N]
   DevBuf<Real> w, V, Vt;       // V column-major [D_all x K]; Vt feature-major mirror
   DevBuf<Real> hyper;          // alpha, w0, mu_w[G], lambda_w[G], mu_V[G*K], lambda_V[G*K]
   DevBuf<Real> scal;           // [0] = w0 delta
@@ -316,24 +322,34 @@ template <typename Real> struct Trainer : TrainerBase {
     for (auto &ev : z_copied)
       MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
+    // dependency levels, device row order, sweep work items (host_data.hpp)
+    {
+      HostCs<Real> Xth0 = host_transpose(Xh);
+      int n_levels = 0, primary = -1;
+      std::vector<int> level = compute_levels(Xth0, &n_levels);
+      perm = primary_row_order(Xth0, level, n_levels, &primary);
+      Xh = permute_rows(Xh, perm);
+      HostCs<Real> Xth = host_transpose(Xh);
+      plan = make_sweep_plan(Xth, level, n_levels, SWEEP_WARP_MAX, SWEEP_CHUNK);
+      plan.primary_level = primary;
+      Xt.upload(Xth, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    }
+    perm_dev.upload(perm, stream);
+    item_col.upload(plan.item_col, stream);
+    item_lo.upload(plan.item_lo, stream);
+    item_hi.upload(plan.item_hi, stream);
+    seg_first.upload(plan.seg_first, stream);
+    seg_count.upload(plan.seg_count, stream);
+    seg_partial.alloc(2 * static_cast<size_t>(std::max(1, plan.max_seg_items)));
+    seg_theta_old.alloc(std::max(1, plan.max_seg_items));
+
     data.launch_counter = &launches;
-    data.build(Xh, n_rel, relations, stream);
+    data.build(Xh, n_rel, relations, stream, &perm);
     N = data.n_rows, D = data.dim_main, D_all = data.dim_all;
     if (static_cast<int64_t>(cfg.group_index.size()) != D_all)
       throw std::invalid_argument("group_index must have one entry per feature.");
     G = cfg.n_groups;
-
-    HostCs<Real> Xth = host_transpose(Xh);
-    Xt.upload(Xth, stream);
-    plan = make_level_plan(Xth, LONG_COLUMN, SEG_NNZ);
-    plan_cols.upload(plan.cols, stream);
-    seg_col.upload(plan.seg_col, stream);
-    seg_lo.upload(plan.seg_lo, stream);
-    seg_hi.upload(plan.seg_hi, stream);
-    seg_slot.upload(plan.seg_slot, stream);
-    slot_ptr.upload(plan.slot_ptr, stream);
-    seg_partial.alloc(2 * static_cast<size_t>(plan.max_segs));
-    seg_theta_old.alloc(plan.max_slots);
 
     rel_train.resize(n_rel);
     for (int b = 0; b < n_rel; b++) {
@@ -356,8 +372,8 @@ template <typename Real> struct Trainer : TrainerBase {
       for (int64_t s = 0; s < S; s++)
         seg_ptr[s + 1] += seg_ptr[s];
       std::vector<int> cur(seg_ptr.begin(), seg_ptr.end() - 1);
-      for (int64_t i = 0; i < N; i++)
-        seg_rows[cur[r.original_to_block[i]]++] = static_cast<int>(i);
+      for (int64_t i = 0; i < N; i++) // i: device row
+        seg_rows[cur[r.original_to_block[perm[i]]]++] = static_cast<int>(i);
       t.seg_ptr.upload(seg_ptr, stream);
       t.seg_rows.upload(seg_rows, stream);
       t.card.upload(card, stream);
@@ -372,12 +388,19 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaStreamSynchronize(stream));
     }
 
-    y_host.resize(N);
-    for (int64_t i = 0; i < N; i++)
-      y_host[i] = static_cast<Real>(y_api[i]);
-    y.upload(y_host, stream);
-    e.alloc(N);
-    q.alloc(N);
+    y_host.resize(N); // caller's row order (the host-side latent draws walk rows in that order)
+    {
+      std::vector<Real> y_dev(N);
+      for (int64_t i = 0; i < N; i++) {
+        y_host[i] = static_cast<Real>(y_api[i]);
+        y_dev[i] = static_cast<Real>(y_api[perm[i]]);
+      }
+      y.upload(y_dev, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    }
+    eq_buf.alloc(2 * static_cast<size_t>(N));
+    eq_buf.zero(stream);
+    dense_tmp.alloc(N);
     group.upload(cfg.group_index, stream);
     feat_ptr.upload(cfg.feat_ptr, stream);
     feat_idx.upload(cfg.feat_idx, stream);
@@ -412,6 +435,9 @@ template <typename Real> struct Trainer : TrainerBase {
   size_t hyper_size() const { return 2 + 2 * static_cast<size_t>(G) + 2 * static_cast<size_t>(G) * K; }
 
   void launched(int n = 1) { launches += n; }
+  Pair<Real> *eq() { return reinterpret_cast<Pair<Real> *>(eq_buf.p); }
+  Real *e_ptr() { return eq_buf.p; }     // stride 2
+  Real *q_ptr() { return eq_buf.p + 1; } // stride 2
 
   // create_FM + create_Hyper (BaseFMTrainer.hpp:107-115), initialize_hyper + initialize_e
   // (FMTrainer.hpp:89-119)
@@ -445,7 +471,7 @@ template <typename Real> struct Trainer : TrainerBase {
     z_dev.alloc(layout.total);
     for (auto &pb : z_pinned)
       pb.alloc(layout.total);
-    data.predict(w.p, Vt.p, K, hv().w0, y.p, e.p);
+    data.predict(w.p, Vt.p, K, hv().w0, y.p, e_ptr(), 2);
     MYFM_CUDA(cudaStreamSynchronize(stream));
     sweep_index = 0;
   }
@@ -495,33 +521,40 @@ template <typename Real> struct Trainer : TrainerBase {
   void sweep_main(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda,
                   const Real *mu) {
     SweepArgs<Real> a;
-    a.Xt = Xt.view();
-    a.e = e.p, a.q = q.p;
+    a.idx = Xt.idx.p, a.val = Xt.val.p;
+    a.eq = eq();
     a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
     a.z = z, a.group = group.p;
     a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
-    for (int lv = 0; lv < plan.n_levels; lv++) {
-      const int base = plan.level_ptr[lv], n = plan.level_ptr[lv + 1] - base;
-      const int n_long = plan.n_long[lv], n_short = n - n_long;
+    a.partial = seg_partial.p, a.theta_old_buf = seg_theta_old.p;
+    for (const SweepLevel &L : plan.levels) {
+      a.item_col = item_col.p + L.s0, a.item_lo = item_lo.p + L.s0, a.item_hi = item_hi.p + L.s0;
+      a.seg_first = seg_first.p + L.s0, a.seg_count = seg_count.p + L.s0;
+      a.nS = L.c0 - L.s0, a.nC = L.w0 - L.c0, a.nW = L.end - L.w0;
+      const int grid = a.nS + a.nC + ceil_div(a.nW, SWEEP_WARPS);
+      if (!grid)
+        continue;
       TimedSpan span(timer, stream, 0);
-      if (n_long) { // segmented two-phase path: no column can serialise the level
-        const int sb = plan.seg_level_ptr[lv], n_seg = plan.seg_level_ptr[lv + 1] - sb;
-        SegPlanView sp{seg_col.p + sb, seg_lo.p + sb, seg_hi.p + sb, seg_slot.p + sb,
-                       slot_ptr.p + plan.slot_level_ptr[lv]};
-        a.cols = nullptr, a.n_cols = 0;
-        k_seg_stats<Real, IS_V><<<n_seg, SEG_THREADS, 0, stream>>>(a, sp, seg_partial.p, seg_theta_old.p);
-        k_seg_update<Real, IS_V><<<n_seg, SEG_THREADS, 0, stream>>>(a, sp, seg_partial.p, seg_theta_old.p);
-        launched(2);
-      }
-      if (n_short) {
-        a.cols = plan_cols.p + base + n_long, a.n_cols = n_short;
-        k_sweep_warp<Real, IS_V><<<ceil_div(static_cast<int64_t>(n_short) * 32, 256), 256, 0, stream>>>(a);
-        launched();
-      }
+#define MYFM_LEVEL(U, C)                                                                           \
+  {                                                                                                \
+    k_level_sweep<Real, IS_V, U, C><<<grid, SWEEP_THREADS, 0, stream>>>(a);                        \
+    if (a.nS)                                                                                      \
+      k_level_seg_update<Real, IS_V, U, C><<<a.nS, SWEEP_THREADS, 0, stream>>>(a);                 \
+  }
+      if (L.unit && L.contig)
+        MYFM_LEVEL(true, true)
+      else if (L.unit)
+        MYFM_LEVEL(true, false)
+      else if (L.contig)
+        MYFM_LEVEL(false, true)
+      else
+        MYFM_LEVEL(false, false)
+#undef MYFM_LEVEL
+      launched(a.nS ? 2 : 1);
     }
   }
 
-  void spmv(const DevCs<Real> &A, const Real *x, Real *out, bool squared) {
+  void spmv(const DevCs<Real> &A, const Real *x, Real *out, bool squared, int out_stride = 1) {
     if (!A.n_major)
       return;
     const int lpr = pow2_ceil_clamped(A.avg_len() / 4.0, 1, 32);
@@ -530,9 +563,9 @@ template <typename Real> struct Trainer : TrainerBase {
 #define MYFM_SPMV(L)                                                                               \
   case L:                                                                                          \
     if (squared)                                                                                   \
-      k_spmv<Real, L, true><<<grid, 256, 0, stream>>>(n, A.view(), x, out);                        \
+      k_spmv<Real, L, true><<<grid, 256, 0, stream>>>(n, A.view(), x, out, out_stride);            \
     else                                                                                           \
-      k_spmv<Real, L, false><<<grid, 256, 0, stream>>>(n, A.view(), x, out);                       \
+      k_spmv<Real, L, false><<<grid, 256, 0, stream>>>(n, A.view(), x, out, out_stride);           \
     break;
     switch (lpr) {
       MYFM_SPMV(1)
@@ -581,13 +614,13 @@ template <typename Real> struct Trainer : TrainerBase {
       spmv(d.B, w.p + d.offset, t.q.p, false);
       if (d.S) {
         k_rel_gather_w<Real><<<ceil_div(d.S * 32, 256), 256, 0, stream>>>(
-            static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), e.p);
+            static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), eq());
         launched();
       }
       rel_sweep<false>(static_cast<int>(b), w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
       spmv(d.B, w.p + d.offset, t.q.p, false);
       if (n) {
-        k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, e.p);
+        k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, e_ptr());
         launched();
       }
     }
@@ -604,15 +637,17 @@ template <typename Real> struct Trainer : TrainerBase {
       {
         TimedSpan span(timer, stream, 1);
         if (D)
-          spmv(data.X, Vr, q.p, false);
-        else
-          q.zero(stream);
+          spmv(data.X, Vr, q_ptr(), false, 2);
+        else if (n) {
+          k_fill_strided<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, q_ptr(), 2, Real(0));
+          launched();
+        }
         for (size_t b = 0; b < data.rels.size(); b++) {
           auto &d = data.rels[b];
           auto &t = rel_train[b];
           spmv(d.B, Vr + d.offset, t.q.p, false);
           if (n) {
-            k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, q.p);
+            k_rel_add_rows<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.q.p, q_ptr());
             launched();
           }
         }
@@ -624,12 +659,12 @@ template <typename Real> struct Trainer : TrainerBase {
         spmv(d.B, Vr + d.offset, t.q_S.p, true);
         if (d.S) {
           k_rel_gather_v<Real><<<ceil_div(d.S * 32, 256), 256, 0, stream>>>(
-              static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), e.p, q.p);
+              static_cast<int>(d.S), t.seg_ptr.p, t.seg_rows.p, t.cache(), eq());
           launched();
         }
         rel_sweep<true>(static_cast<int>(b), Vr, Vt.p + r, K, z, lam, mu);
         if (n) {
-          k_rel_resync_v<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.cache(), e.p, q.p);
+          k_rel_resync_v<Real><<<ceil_div(n, 256), 256, 0, stream>>>(n, d.map.p, t.cache(), eq());
           launched();
         }
       }
@@ -639,17 +674,32 @@ template <typename Real> struct Trainer : TrainerBase {
   // update_e for classification (FMTrainer.hpp:498-512): the truncated-normal draws consume the
   // mt19937 stream row by row, data dependently, so in MT19937 mode they run on the host.
   void classification_latent() {
-    MYFM_CUDA(cudaStreamSynchronize(stream));
     e_host.resize(N);
-    e.download(e_host.data(), N, stream);
-    MYFM_CUDA(cudaStreamSynchronize(stream));
+    export_component(0, e_host.data()); // caller's row order: the stream is consumed row by row
     const Real zero = 0, sd = 1;
     for (int64_t i = 0; i < N; i++) {
       Real pred = e_host[i];
       Real n = y_host[i] > 0 ? rng.tn_left(pred, sd, zero) : rng.tn_right(pred, sd, zero);
       e_host[i] -= n;
     }
-    e.upload(e_host.data(), N, stream);
+    import_component(0, e_host.data());
+  }
+
+  // eq component (0 = e, 1 = q) <-> a dense host vector in the caller's row order
+  void export_component(int comp, Real *host) {
+    if (!N)
+      return;
+    k_eq_export<Real><<<ceil_div(N, 256), 256, 0, stream>>>(N, eq_buf.p, comp, perm_dev.p, dense_tmp.p);
+    launched();
+    dense_tmp.download(host, N, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+  void import_component(int comp, const Real *host) {
+    if (!N)
+      return;
+    dense_tmp.upload(host, N, stream);
+    k_eq_import<Real><<<ceil_div(N, 256), 256, 0, stream>>>(N, eq_buf.p, comp, perm_dev.p, dense_tmp.p);
+    launched();
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
 
@@ -667,17 +717,17 @@ template <typename Real> struct Trainer : TrainerBase {
     const SweepLayout &L = layout;
 
     if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
-      k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, e.p, h.w0, partial.p);
+      k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
       k_finish_alpha<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p,
                                                    static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha);
       launched(2);
     }
     if (cfg.fit_w0) { // update_w0
-      k_reduce_e<Real, 1><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, e.p, h.w0, partial.p);
+      k_reduce_e<Real, 1><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
       k_finish_w0<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p, static_cast<int>(N),
                                                 static_cast<Real>(cfg.reg_0), h.alpha, z + L.z_w0, h.w0,
                                                 scal.p);
-      k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, e.p, scal.p);
+      k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, eq(), scal.p);
       launched(3);
     } else {
       MYFM_CUDA(cudaMemsetAsync(h.w0, 0, sizeof(Real), stream));
@@ -699,7 +749,7 @@ template <typename Real> struct Trainer : TrainerBase {
     update_V(z + L.z_V);
     { // update_e
       TimedSpan span(timer, stream, 2);
-      data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e.p);
+      data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e_ptr(), 2);
     }
     if (cfg.task_type == MYFM_TASK_CLASSIFICATION)
       classification_latent();
@@ -777,12 +827,14 @@ template <typename Real> struct Trainer : TrainerBase {
                                     lambda_V[static_cast<size_t>(g) * K + r] = lv[g + static_cast<size_t>(G) * r];
   }
   void get_e(double *out) override {
-    auto h = fetch(e.p, N);
+    std::vector<Real> h(N);
+    export_component(0, h.data());
     for (int64_t i = 0; i < N; i++)
       out[i] = h[i];
   }
   void get_q(double *out) override {
-    auto h = fetch(q.p, N);
+    std::vector<Real> h(N);
+    export_component(1, h.data());
     for (int64_t i = 0; i < N; i++)
       out[i] = h[i];
   }
@@ -833,7 +885,7 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     if (e_in) {
       tmp.assign(e_in, e_in + N);
-      e.upload(tmp, stream);
+      import_component(0, tmp.data());
     }
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }

@@ -173,6 +173,131 @@ LevelPlan make_level_plan(const HostCs<Real> &csc, int long_threshold, int seg_n
   return plan;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Main-table sweep plan (engine.cu: Trainer).
+//
+// Row order.  The sampler's result does not depend on the order of the training rows (only the
+// order of summation inside a column does, at rounding level), so the engine stores rows in its
+// own order: rows are grouped by their column in the PRIMARY level (the dependency level that
+// holds the most entries; for one-hot fields the first field), columns ascending, original row
+// order inside a column, rows without an entry in that level last.  In that order every column of
+// the primary level is a contiguous row range: its sweep streams instead of gathering.
+//
+// Work items.  Per level, columns are split by length into
+//   S: columns longer than `chunk` entries, cut into chunks of `chunk` entries; two-phase
+//      (chunk statistics -> ordered reduction + draw + update), one CTA per chunk;
+//   C: columns of (warp_max, chunk] entries, one CTA each, single pass with the gathered values
+//      kept in registers between the reduction and the update;
+//   W: columns of at most warp_max entries, one warp each, likewise.
+// Items of a level are stored S first, then C, then W, each by descending length.
+// ------------------------------------------------------------------------------------------------
+struct SweepLevel {
+  int s0 = 0, c0 = 0, w0 = 0, end = 0; // item ranges [s0,c0) S, [c0,w0) C, [w0,end) W
+  bool unit = true;                    // every value of the level is exactly 1
+  bool contig = true;                  // every column of the level is a contiguous row range
+  int64_t nnz = 0;
+};
+
+struct SweepPlan {
+  std::vector<SweepLevel> levels;
+  std::vector<int> item_col, item_lo, item_hi; // entry range [lo, hi) in the CSC arrays
+  std::vector<int> seg_first, seg_count;       // S items: first chunk item of the column, #chunks
+  int max_seg_items = 0;
+  int primary_level = -1;
+};
+
+// perm[i'] = original row stored at device row i'.
+template <typename Real>
+std::vector<int> primary_row_order(const HostCs<Real> &csc, const std::vector<int> &level,
+                                   int n_levels, int *primary_level) {
+  const int64_t n_rows = csc.n_minor;
+  std::vector<int64_t> level_nnz(std::max(n_levels, 1), 0);
+  for (int64_t j = 0; j < csc.n_major; j++)
+    level_nnz[level[j]] += csc.ptr[j + 1] - csc.ptr[j];
+  int best = -1;
+  for (int l = 0; l < n_levels; l++)
+    if (level_nnz[l] > 0 && (best < 0 || level_nnz[l] > level_nnz[best]))
+      best = l;
+  *primary_level = best;
+  std::vector<int> perm;
+  perm.reserve(n_rows);
+  std::vector<char> taken(n_rows, 0);
+  if (best >= 0)
+    for (int64_t j = 0; j < csc.n_major; j++)
+      if (level[j] == best)
+        for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++) {
+          perm.push_back(csc.idx[p]);
+          taken[csc.idx[p]] = 1;
+        }
+  for (int64_t i = 0; i < n_rows; i++)
+    if (!taken[i])
+      perm.push_back(static_cast<int>(i));
+  return perm;
+}
+
+template <typename Real>
+HostCs<Real> permute_rows(const HostCs<Real> &csr, const std::vector<int> &perm) {
+  HostCs<Real> out;
+  out.n_major = csr.n_major, out.n_minor = csr.n_minor;
+  out.ptr.resize(csr.n_major + 1);
+  out.idx.resize(csr.idx.size());
+  out.val.resize(csr.val.size());
+  out.ptr[0] = 0;
+  for (int64_t i = 0; i < csr.n_major; i++) {
+    const int src = perm[i], b = csr.ptr[src], n = csr.ptr[src + 1] - b, dst = out.ptr[i];
+    std::copy(csr.idx.begin() + b, csr.idx.begin() + b + n, out.idx.begin() + dst);
+    std::copy(csr.val.begin() + b, csr.val.begin() + b + n, out.val.begin() + dst);
+    out.ptr[i + 1] = dst + n;
+  }
+  return out;
+}
+
+template <typename Real>
+SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level, int n_levels,
+                          int warp_max, int chunk) {
+  SweepPlan plan;
+  plan.levels.resize(n_levels);
+  std::vector<std::vector<int>> cols(n_levels);
+  for (int64_t j = 0; j < csc.n_major; j++)
+    cols[level[j]].push_back(static_cast<int>(j));
+  auto len = [&](int j) { return csc.ptr[j + 1] - csc.ptr[j]; };
+  for (int l = 0; l < n_levels; l++) {
+    SweepLevel &L = plan.levels[l];
+    std::vector<int> &c = cols[l];
+    std::stable_sort(c.begin(), c.end(), [&](int x, int y) { return len(x) > len(y); });
+    for (int j : c) {
+      L.nnz += len(j);
+      for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++) {
+        if (csc.val[p] != Real(1))
+          L.unit = false;
+        if (csc.idx[p] != csc.idx[csc.ptr[j]] + (p - csc.ptr[j]))
+          L.contig = false;
+      }
+    }
+    L.s0 = static_cast<int>(plan.item_col.size());
+    auto push = [&](int j, int lo, int hi, int first, int count) {
+      plan.item_col.push_back(j), plan.item_lo.push_back(lo), plan.item_hi.push_back(hi);
+      plan.seg_first.push_back(first), plan.seg_count.push_back(count);
+    };
+    size_t k = 0;
+    for (; k < c.size() && len(c[k]) > chunk; k++) {
+      const int j = c[k], n = (len(j) + chunk - 1) / chunk;
+      const int first = static_cast<int>(plan.item_col.size()) - L.s0; // level-relative
+      for (int s = 0; s < n; s++)
+        push(j, csc.ptr[j] + s * chunk, std::min(csc.ptr[j] + (s + 1) * chunk, csc.ptr[j + 1]), first, n);
+    }
+    L.c0 = static_cast<int>(plan.item_col.size());
+    for (; k < c.size() && len(c[k]) > warp_max; k++)
+      push(c[k], csc.ptr[c[k]], csc.ptr[c[k] + 1], 0, 0);
+    L.w0 = static_cast<int>(plan.item_col.size());
+    for (; k < c.size(); k++)
+      push(c[k], csc.ptr[c[k]], csc.ptr[c[k] + 1], 0, 0);
+    L.end = static_cast<int>(plan.item_col.size());
+    plan.max_seg_items = std::max(plan.max_seg_items, L.c0 - L.s0);
+  }
+  return plan;
+}
+
 // FMLearningConfig (FMLearningConfig.hpp:17-57) after validation.
 struct Config {
   double alpha_0, beta_0, gamma_0, mu_0, reg_0;

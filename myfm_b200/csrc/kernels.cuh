@@ -14,6 +14,13 @@ namespace myfm {
 
 constexpr int MAX_REL = 8; // relation blocks per model
 
+// The residual cache e and the factor cache q of the training rows live interleaved:
+// eq[i] = {e_i, q_i} (see the column sweeps below).
+template <typename Real> struct PairOf;
+template <> struct PairOf<float> { using type = float2; };
+template <> struct PairOf<double> { using type = double2; };
+template <typename Real> using Pair = typename PairOf<Real>::type; // .x = e, .y = q
+
 template <typename Real> struct CsView { // CSR or CSC, device pointers
   const int *ptr = nullptr;
   const int *idx = nullptr;
@@ -40,7 +47,7 @@ template <typename Real> struct RelPredictPack {
 // ----------------------------------------------------------------------------------------------
 template <typename Real, int LPR, bool SQUARED>
 __global__ void __launch_bounds__(256) k_spmv(int n_rows, CsView<Real> A, const Real *__restrict__ x,
-                                               Real *__restrict__ out) {
+                                               Real *__restrict__ out, int out_stride) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LPR, sub = tid % LPR;
   Real acc = 0;
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(256) k_spmv(int n_rows, CsView<Real> A, const 
   }
   acc = subwarp_sum<Real, LPR>(acc);
   if (row < n_rows && sub == 0)
-    out[row] = acc;
+    out[static_cast<size_t>(row) * out_stride] = acc;
 }
 
 // Block tables for the forward pass, one launch per block: warp per block row, lanes over factors.
@@ -94,7 +101,7 @@ template <typename Real, int LPR>
 __global__ void __launch_bounds__(256)
     k_predict(int n_rows, CsView<Real> X, const Real *__restrict__ w, const Real *__restrict__ Vt,
               int K, const Real *__restrict__ w0_ptr, RelPredictPack<Real> rels,
-              const Real *__restrict__ y, Real *__restrict__ out) {
+              const Real *__restrict__ y, Real *__restrict__ out, int out_stride) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LPR, sub = tid % LPR;
   Real lin = 0, acc = 0;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(256)
   acc = subwarp_sum<Real, LPR>(acc);
   if (row < n_rows && sub == 0) {
     Real t = (*w0_ptr + lin) + acc;
-    out[row] = y ? t - y[row] : t;
+    out[static_cast<size_t>(row) * out_stride] = y ? t - y[row] : t;
   }
 }
 
@@ -152,14 +159,14 @@ template <typename Real> struct HyperView {
 // MODE 0: e^2 (update_alpha, FMTrainer.hpp:138)   MODE 1: (w0 - e) (update_w0, :223)
 template <typename Real, int MODE>
 __global__ void __launch_bounds__(512)
-    k_reduce_e(int64_t n, const Real *__restrict__ e, const Real *__restrict__ w0_ptr,
+    k_reduce_e(int64_t n, const Pair<Real> *__restrict__ eq, const Real *__restrict__ w0_ptr,
                Real *__restrict__ partial) {
   __shared__ Real scratch[32];
   Real acc = 0;
   const Real w0 = MODE == 1 ? *w0_ptr : Real(0);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    Real v = e[i];
+    Real v = eq[i].x;
     acc += MODE == 0 ? v * v : (w0 - v);
   }
   acc = block_sum(acc, scratch);
@@ -205,11 +212,11 @@ __global__ void k_finish_w0(int n_partial, const Real *__restrict__ partial, int
 
 template <typename Real>
 __global__ void __launch_bounds__(256)
-    k_add_scalar(int64_t n, Real *__restrict__ e, const Real *__restrict__ delta) {
+    k_add_scalar(int64_t n, Pair<Real> *__restrict__ eq, const Real *__restrict__ delta) {
   const Real d = *delta;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    e[i] += d;
+    eq[i].x += d;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -253,63 +260,53 @@ __global__ void __launch_bounds__(256)
 }
 
 // ----------------------------------------------------------------------------------------------
-// Column sweeps over one dependency level of the main table.  `cols` lists the level's columns;
-// they are pairwise row-disjoint, so the concurrent read-modify-write of e / q below is the
-// reference's serial loop, bit for bit, in any interleaving.
+// Column sweeps over one dependency level of the main table.  The columns of a level are pairwise
+// row-disjoint, so the concurrent read-modify-write of e / q below is the reference's serial
+// loop, bit for bit, in any interleaving.
 //
 // V (FMTrainer.hpp:343-376):  h = x (q - x v_old);  sq = sum h^2;  lin = sum -e h + sq v_old
 //   v_new = draw(alpha sq + lambda, alpha lin + lambda mu);  q += x d;  e += h d
 // w (FMTrainer.hpp:237-254):  e' = e - x w_old;  sq = lambda + alpha sum x^2;
 //   lin = sum (-alpha x) e' + lambda mu;  e = e' + x w_new
+//
+// e and q live interleaved, eq[i] = {e_i, q_i}: a column entry touches ONE 32-byte sector per
+// row instead of two.  Index / value streams are read once with evict-first loads; eq goes
+// through L2 only (no reuse inside a launch), where the f32 working set of the C4 workload
+// (80 MB) stays resident between levels.
+// Work items (host_data.hpp: SweepPlan): S = chunk of a long column (two-phase), C = whole
+// column per CTA, W = whole column per warp; C and W keep the gathered entries in registers
+// between the reduction and the update, so each entry is gathered once and scattered once.
+// UNIT: all values of the level are 1 (val stream not read).  CONTIG: every column is a
+// contiguous row range (idx stream not read; the primary level after the row reordering).
 // ----------------------------------------------------------------------------------------------
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_R = 8;                            // entries per thread held in registers
+constexpr int SWEEP_WARP_MAX = 32 * SWEEP_R;          // longest column of a W item
+constexpr int SWEEP_CHUNK = SWEEP_THREADS * SWEEP_R;  // longest column of a C item / chunk size
+constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
+
 template <typename Real> struct SweepArgs {
-  CsView<Real> Xt;     // CSC of the main table
-  const int *cols;     // columns of this launch
-  int n_cols;
-  Real *e;
-  Real *q;             // unused for w
-  Real *theta;         // w, or column r of V (column-major)
-  Real *theta_t;       // feature-major mirror: theta_t[j * t_stride], or nullptr
+  const int *idx;       // CSC entry arrays of the main table (device row order)
+  const Real *val;
+  const int *item_col;  // work items of THIS level (already offset to the level's first item)
+  const int *item_lo;
+  const int *item_hi;
+  const int *seg_first; // S items: first chunk of the column (level-relative), chunk count
+  const int *seg_count;
+  int nS, nC, nW;
+  Pair<Real> *eq;
+  Real *theta;          // w, or column r of V (column-major)
+  Real *theta_t;        // feature-major mirror: theta_t[j * t_stride], or nullptr
   int64_t t_stride;
-  const Real *z;       // standardised normals indexed by feature
-  const int *group;    // group of every feature
+  const Real *z;        // standardised normals indexed by feature
+  const int *group;     // group of every feature
   const Real *alpha;
-  const Real *lambda;  // [G] of this vector
-  const Real *mu;      // [G]
+  const Real *lambda;   // [G] of this vector
+  const Real *mu;       // [G]
+  Real *partial;        // [2 * nS] chunk statistics
+  Real *theta_old_buf;  // [nS] value before the update, written by a column's first chunk
 };
-
-template <typename Real, bool IS_V>
-__device__ __forceinline__ void column_pass1(const CsView<Real> &Xt, int p, Real theta_old,
-                                             const Real *e, const Real *q, Real alpha, Real &sq,
-                                             Real &lin) {
-  const int i = Xt.idx[p];
-  const Real x = Xt.val[p];
-  if (IS_V) {
-    Real h = x * (q[i] - x * theta_old);
-    sq += h * h;
-    lin += (-e[i]) * h;
-  } else {
-    Real e1 = e[i] - x * theta_old;
-    sq += x * x;
-    lin += ((-alpha) * x) * e1;
-  }
-}
-
-template <typename Real, bool IS_V>
-__device__ __forceinline__ void column_pass2(const CsView<Real> &Xt, int p, Real theta_old,
-                                             Real theta_new, Real *e, Real *q) {
-  const int i = Xt.idx[p];
-  const Real x = Xt.val[p];
-  if (IS_V) {
-    Real qi = q[i];
-    Real h = x * (qi - x * theta_old);
-    q[i] = qi + x * (theta_new - theta_old);
-    e[i] += h * (theta_new - theta_old);
-  } else {
-    Real e1 = e[i] - x * theta_old;
-    e[i] = e1 + x * theta_new;
-  }
-}
 
 template <typename Real, bool IS_V>
 __device__ __forceinline__ Real column_draw(Real sq, Real lin, Real theta_old, Real alpha, Real lam,
@@ -327,117 +324,157 @@ __device__ __forceinline__ Real column_draw(Real sq, Real lin, Real theta_old, R
   return (lin / sq) + z / sqrt(sq);
 }
 
-// One warp per column (short columns).
-template <typename Real, bool IS_V>
-__global__ void __launch_bounds__(256) k_sweep_warp(SweepArgs<Real> a) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= a.n_cols)
-    return;
-  const int j = a.cols[c];
-  const int b = a.Xt.ptr[j], en = a.Xt.ptr[j + 1];
-  const Real theta_old = a.theta[j];
-  const Real alpha = *a.alpha;
-  Real sq = 0, lin = 0;
-#pragma unroll 4
-  for (int p = b + lane; p < en; p += 32)
-    column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
-  sq = warp_sum(sq);
-  lin = warp_sum(lin);
-  const int g = a.group[j];
-  const Real theta_new =
-      column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
-  if (lane == 0) {
-    a.theta[j] = theta_new;
-    if (a.theta_t)
-      a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+// The entries one thread owns: t, t + NT, t + 2 NT, ... of [lo, hi).
+template <typename Real, bool IS_V, bool UNIT, bool CONTIG, int NT> struct ColumnEntries {
+  int i[SWEEP_R];
+  Real x[SWEEP_R], e[SWEEP_R], q[SWEEP_R];
+
+  __device__ __forceinline__ void load(const SweepArgs<Real> &a, int lo, int hi, int t) {
+    int first = 0;
+    if (CONTIG)
+      first = lo < hi ? a.idx[lo] : 0;
+#pragma unroll
+    for (int s = 0; s < SWEEP_R; s++) {
+      const int p = lo + t + s * NT;
+      const bool ok = p < hi;
+      i[s] = ok ? (CONTIG ? first + (p - lo) : __ldcs(a.idx + p)) : -1;
+      x[s] = UNIT ? Real(1) : (ok ? __ldcs(a.val + p) : Real(0));
+    }
+#pragma unroll
+    for (int s = 0; s < SWEEP_R; s++) {
+      e[s] = 0, q[s] = 0;
+      if (i[s] >= 0) {
+        const Pair<Real> v = __ldcg(a.eq + i[s]);
+        e[s] = v.x, q[s] = v.y;
+      }
+    }
   }
-#pragma unroll 4
-  for (int p = b + lane; p < en; p += 32)
-    column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
-}
 
-// Long columns are cut into segments of SEG_NNZ entries, one thread block each, so that a heavy
-// tail (one movie rated by 3 % of all rows) cannot serialise a level on one SM:
-//   k_seg_stats : per-segment partial (sum h^2, sum -e h)            -> partial[seg]
-//   k_seg_update: every segment of a column sums that column's partials in segment order
-//                 (deterministic, identical in every block), draws, and updates its own rows.
-// The same stats -> (reduce) -> update split is what row-sharded multi-GPU training needs.
-constexpr int SEG_THREADS = 256;
-constexpr int SEG_PER_THREAD = 4;
-constexpr int SEG_NNZ = SEG_THREADS * SEG_PER_THREAD;
+  __device__ __forceinline__ void stats(Real theta_old, Real alpha, Real &sq, Real &lin) const {
+#pragma unroll
+    for (int s = 0; s < SWEEP_R; s++)
+      if (i[s] >= 0) {
+        if (IS_V) {
+          Real h = x[s] * (q[s] - x[s] * theta_old);
+          sq += h * h;
+          lin += (-e[s]) * h;
+        } else {
+          Real e1 = e[s] - x[s] * theta_old;
+          sq += x[s] * x[s];
+          lin += ((-alpha) * x[s]) * e1;
+        }
+      }
+  }
 
-struct SegPlanView {
-  const int *seg_col;   // [n_seg] column of the segment
-  const int *seg_lo;    // [n_seg] first entry (absolute position in the CSC arrays)
-  const int *seg_hi;    // [n_seg] one past the last entry
-  const int *seg_slot;  // [n_seg] index of the column among the launch's long columns
-  const int *slot_ptr;  // [n_slots + 1] segments of each long column
+  __device__ __forceinline__ void update(const SweepArgs<Real> &a, Real theta_old,
+                                         Real theta_new) const {
+#pragma unroll
+    for (int s = 0; s < SWEEP_R; s++)
+      if (i[s] >= 0) {
+        Pair<Real> v;
+        if (IS_V) {
+          Real h = x[s] * (q[s] - x[s] * theta_old);
+          v.y = q[s] + x[s] * (theta_new - theta_old);
+          v.x = e[s] + h * (theta_new - theta_old);
+        } else {
+          Real e1 = e[s] - x[s] * theta_old;
+          v.x = e1 + x[s] * theta_new;
+          v.y = q[s];
+        }
+        __stcg(a.eq + i[s], v);
+      }
+  }
 };
 
-template <typename Real, bool IS_V>
-__global__ void __launch_bounds__(SEG_THREADS)
-    k_seg_stats(SweepArgs<Real> a, SegPlanView sp, Real *__restrict__ partial,
-                Real *__restrict__ theta_old_buf) {
+template <typename Real>
+__device__ __forceinline__ void store_theta(const SweepArgs<Real> &a, int j, Real theta_new) {
+  a.theta[j] = theta_new;
+  if (a.theta_t)
+    a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+}
+
+// One launch per level: blocks [0, nS) chunk statistics, [nS, nS+nC) one column per CTA, the rest
+// eight columns per CTA (one per warp).
+template <typename Real, bool IS_V, bool UNIT, bool CONTIG>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_level_sweep(SweepArgs<Real> a) {
   __shared__ Real scratch[32];
-  const int s = blockIdx.x;
-  const int j = sp.seg_col[s];
-  const int lo = sp.seg_lo[s], hi = sp.seg_hi[s];
-  const Real theta_old = a.theta[j];
+  const int b = blockIdx.x;
   const Real alpha = *a.alpha;
-  Real sq = 0, lin = 0;
-#pragma unroll
-  for (int k = 0; k < SEG_PER_THREAD; k++) {
-    const int p = lo + threadIdx.x + k * SEG_THREADS;
-    if (p < hi)
-      column_pass1<Real, IS_V>(a.Xt, p, theta_old, a.e, a.q, alpha, sq, lin);
-  }
-  sq = block_sum(sq, scratch);
-  lin = block_sum(lin, scratch);
-  if (threadIdx.x == 0) {
-    partial[2 * s] = sq;
-    partial[2 * s + 1] = lin;
-    if (sp.slot_ptr[sp.seg_slot[s]] == s) // first segment snapshots the old value for the update
-      theta_old_buf[sp.seg_slot[s]] = theta_old;
+  if (b < a.nS + a.nC) {
+    const int j = a.item_col[b];
+    const Real theta_old = a.theta[j];
+    ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
+    en.load(a, a.item_lo[b], a.item_hi[b], threadIdx.x);
+    Real sq = 0, lin = 0;
+    en.stats(theta_old, alpha, sq, lin);
+    sq = block_sum(sq, scratch);
+    lin = block_sum(lin, scratch);
+    if (b < a.nS) { // long column: the update runs in k_level_seg_update
+      if (threadIdx.x == 0) {
+        a.partial[2 * b] = sq;
+        a.partial[2 * b + 1] = lin;
+        if (a.seg_first[b] == b)
+          a.theta_old_buf[b] = theta_old;
+      }
+      return;
+    }
+    const int g = a.group[j];
+    const Real theta_new =
+        column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+    if (threadIdx.x == 0)
+      store_theta(a, j, theta_new);
+    en.update(a, theta_old, theta_new);
+  } else {
+    const int w = (b - a.nS - a.nC) * SWEEP_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= a.nW)
+      return;
+    const int it = a.nS + a.nC + w;
+    const int j = a.item_col[it];
+    const Real theta_old = a.theta[j];
+    ColumnEntries<Real, IS_V, UNIT, CONTIG, 32> en;
+    en.load(a, a.item_lo[it], a.item_hi[it], lane);
+    Real sq = 0, lin = 0;
+    en.stats(theta_old, alpha, sq, lin);
+    sq = warp_sum(sq);
+    lin = warp_sum(lin);
+    const int g = a.group[j];
+    const Real theta_new =
+        column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+    if (lane == 0)
+      store_theta(a, j, theta_new);
+    en.update(a, theta_old, theta_new);
   }
 }
 
-template <typename Real, bool IS_V>
-__global__ void __launch_bounds__(SEG_THREADS)
-    k_seg_update(SweepArgs<Real> a, SegPlanView sp, const Real *__restrict__ partial,
-                 const Real *__restrict__ theta_old_buf) {
+// Second phase of the long columns: every chunk sums its column's chunk statistics in chunk
+// order (deterministic, identical in every CTA), draws, and updates its own entries.
+template <typename Real, bool IS_V, bool UNIT, bool CONTIG>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_level_seg_update(SweepArgs<Real> a) {
   __shared__ Real bcast[2];
-  const int s = blockIdx.x;
-  const int j = sp.seg_col[s];
-  const int slot = sp.seg_slot[s];
-  const int first = sp.slot_ptr[slot], last = sp.slot_ptr[slot + 1];
+  const int b = blockIdx.x;
+  const int j = a.item_col[b];
+  const int first = a.seg_first[b], last = first + a.seg_count[b];
   if (threadIdx.x < 32) {
     Real sq = 0, lin = 0;
     for (int i = first + threadIdx.x; i < last; i += 32) {
-      sq += partial[2 * i];
-      lin += partial[2 * i + 1];
+      sq += a.partial[2 * i];
+      lin += a.partial[2 * i + 1];
     }
     sq = warp_sum(sq);
     lin = warp_sum(lin);
     if (threadIdx.x == 0)
       bcast[0] = sq, bcast[1] = lin;
   }
+  ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
+  en.load(a, a.item_lo[b], a.item_hi[b], threadIdx.x);
   __syncthreads();
-  const Real theta_old = theta_old_buf[slot];
+  const Real theta_old = a.theta_old_buf[first];
   const int g = a.group[j];
   const Real theta_new = column_draw<Real, IS_V>(bcast[0], bcast[1], theta_old, *a.alpha,
                                                  a.lambda[g], a.mu[g], a.z[j]);
-  if (s == first && threadIdx.x == 0) {
-    a.theta[j] = theta_new;
-    if (a.theta_t)
-      a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
-  }
-  const int lo = sp.seg_lo[s], hi = sp.seg_hi[s];
-#pragma unroll
-  for (int k = 0; k < SEG_PER_THREAD; k++) {
-    const int p = lo + threadIdx.x + k * SEG_THREADS;
-    if (p < hi)
-      column_pass2<Real, IS_V>(a.Xt, p, theta_old, theta_new, a.e, a.q);
-  }
+  if (b == first && threadIdx.x == 0)
+    store_theta(a, j, theta_new);
+  en.update(a, theta_old, theta_new);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -454,17 +491,17 @@ template <typename Real> struct RelCache {
 template <typename Real>
 __global__ void __launch_bounds__(256)
     k_rel_add_rows(int n, const int *__restrict__ map, const Real *__restrict__ blk,
-                   Real *__restrict__ out) {
+                   Real *__restrict__ out) { // out: the e or the q component of eq (stride 2)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
-    out[i] += blk[map[i]];
+    out[2 * static_cast<size_t>(i)] += blk[map[i]];
 }
 
 // w part, FMTrainer.hpp:268-275: E[s] = sum e_i ; e_i -= qB[s].  Warp per block row.
 template <typename Real>
 __global__ void __launch_bounds__(256)
     k_rel_gather_w(int S, const int *__restrict__ seg_ptr, const int *__restrict__ seg_rows,
-                   RelCache<Real> cache, Real *__restrict__ e) {
+                   RelCache<Real> cache, Pair<Real> *__restrict__ eq) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= S)
     return;
@@ -472,9 +509,9 @@ __global__ void __launch_bounds__(256)
   Real acc = 0;
   for (int k = seg_ptr[s] + lane; k < seg_ptr[s + 1]; k += 32) {
     const int i = seg_rows[k];
-    Real ei = e[i];
+    Real ei = eq[i].x;
     acc += ei;
-    e[i] = ei - qb;
+    eq[i].x = ei - qb;
   }
   acc = warp_sum(acc);
   if (lane == 0)
@@ -485,7 +522,7 @@ __global__ void __launch_bounds__(256)
 template <typename Real>
 __global__ void __launch_bounds__(256)
     k_rel_gather_v(int S, const int *__restrict__ seg_ptr, const int *__restrict__ seg_rows,
-                   RelCache<Real> cache, Real *__restrict__ e, Real *__restrict__ q) {
+                   RelCache<Real> cache, Pair<Real> *__restrict__ eq) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= S)
     return;
@@ -493,15 +530,17 @@ __global__ void __launch_bounds__(256)
   Real c = 0, c_S = 0, es = 0, e_q = 0;
   for (int k = seg_ptr[s] + lane; k < seg_ptr[s + 1]; k += 32) {
     const int i = seg_rows[k];
-    Real ei = e[i];
-    Real temp = (q[i] - qb);
+    Pair<Real> v = eq[i];
+    Real ei = v.x;
+    Real temp = (v.y - qb);
     c += temp;
     c_S += temp * temp;
     es += ei;
     e_q += ei * temp;
-    q[i] = temp;
+    v.y = temp;
     // 0.5 is a double literal in the reference: this expression is evaluated in double
-    e[i] = static_cast<Real>(ei - (temp * qb + 0.5 * qb * qb - 0.5 * qs));
+    v.x = static_cast<Real>(ei - (temp * qb + 0.5 * qb * qb - 0.5 * qs));
+    eq[i] = v;
   }
   c = warp_sum(c), c_S = warp_sum(c_S), es = warp_sum(es), e_q = warp_sum(e_q);
   if (lane == 0)
@@ -511,15 +550,17 @@ __global__ void __launch_bounds__(256)
 // FMTrainer.hpp:473-480
 template <typename Real>
 __global__ void __launch_bounds__(256)
-    k_rel_resync_v(int n, const int *__restrict__ map, RelCache<Real> cache, Real *__restrict__ e,
-                   Real *__restrict__ q) {
+    k_rel_resync_v(int n, const int *__restrict__ map, RelCache<Real> cache,
+                   Pair<Real> *__restrict__ eq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   const int s = map[i];
-  const Real qb = cache.q[s], qs = cache.q_S[s], qi = q[i];
-  e[i] = static_cast<Real>(e[i] + (qi * qb + 0.5 * qb * qb - 0.5 * qs));
-  q[i] = qi + qb;
+  Pair<Real> v = eq[i];
+  const Real qb = cache.q[s], qs = cache.q_S[s], qi = v.y;
+  v.x = static_cast<Real>(v.x + (qi * qb + 0.5 * qb * qb - 0.5 * qs));
+  v.y = qi + qb;
+  eq[i] = v;
 }
 
 // Sweep over the columns of one block, in dependency levels of the block rows.  The chain of
@@ -647,6 +688,25 @@ __global__ void __launch_bounds__(1024) k_rel_sweep(RelSweepArgs<Real> a) {
 // ----------------------------------------------------------------------------------------------
 // Small utilities
 // ----------------------------------------------------------------------------------------------
+// Boundary copies of one component of eq between device row order and the caller's row order:
+// dense[perm[i]] = eq[i].c  /  eq[i].c = dense[perm[i]]   (comp 0 = e, 1 = q)
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_eq_export(int64_t n, const Real *__restrict__ eq, int comp, const int *__restrict__ perm,
+                Real *__restrict__ dense) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    dense[perm[i]] = eq[2 * i + comp];
+}
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_eq_import(int64_t n, Real *__restrict__ eq, int comp, const int *__restrict__ perm,
+                const Real *__restrict__ dense) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    eq[2 * i + comp] = dense[perm[i]];
+}
+
 // Vt[j*K + r] = V[j + D*r]
 template <typename Real>
 __global__ void __launch_bounds__(256)
@@ -657,6 +717,13 @@ __global__ void __launch_bounds__(256)
     const int r = static_cast<int>(t % K);
     Vt[t] = V[j + D * r];
   }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_fill_strided(int64_t n, Real *p, int stride, Real v) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    p[i * stride] = v;
 }
 
 template <typename Real>
