@@ -148,6 +148,10 @@ int myfm_trainer_get_q(myfm_trainer_t *t, double *q);
 int myfm_trainer_set_state(myfm_trainer_t *t, const double *w0, const double *w, const double *V,
                            const double *alpha, const double *mu_w, const double *lambda_w,
                            const double *mu_V, const double *lambda_V, const double *e);
+/* The standardised variates (N(0,1) / Gamma(shape,1)) the most recent sweep consumed, in the
+ * reference's draw order (BaseFMTrainer.hpp:135-152); writes their number to *n and copies them
+ * when capacity suffices.  RNG tests compare them with myfm_rng_fill. */
+int myfm_trainer_get_variates(myfm_trainer_t *t, double *out, int64_t capacity, int64_t *n);
 /* OprobitSampler::accept_count of cutpoint group g (FMTrainer.hpp:83-85) */
 int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count);
 /* number of kernels this trainer has launched so far (bench.py's gpu_launches) */

@@ -86,7 +86,7 @@ EXPORTS = [
     "myfm_trainer_create", "myfm_trainer_destroy", "myfm_trainer_init_fm", "myfm_trainer_step",
     "myfm_trainer_sync", "myfm_trainer_timed_steps", "myfm_trainer_dims", "myfm_trainer_get_fm", "myfm_trainer_get_cutpoints",
     "myfm_trainer_get_hyper", "myfm_trainer_get_e", "myfm_trainer_get_q", "myfm_trainer_set_state",
-    "myfm_trainer_mh_accept",
+    "myfm_trainer_mh_accept", "myfm_trainer_get_variates",
     "myfm_trainer_launch_count", "myfm_trainer_kernel_ms", "myfm_trainer_set_profiling",
     "myfm_dataset_create", "myfm_dataset_destroy", "myfm_predict_score", "myfm_predict_mean",
     "myfm_predict_oprobit_mean", "myfm_trainer_predict_score", "myfm_rng_fill",

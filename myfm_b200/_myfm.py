@@ -627,6 +627,14 @@ class _TrainerHandle:
             arr(hyper.mu_V) if hyper is not None else None,
             arr(hyper.lambda_V) if hyper is not None else None, arr(e)))
 
+    def get_variates(self) -> np.ndarray:
+        """Standardised variates the most recent sweep consumed (reference draw order)."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().myfm_trainer_get_variates(self._h, None, C.c_int64(0), C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        _lib.check(_lib.lib().myfm_trainer_get_variates(self._h, _lib.vptr(out), C.c_int64(n.value), C.byref(n)))
+        return out
+
     def mh_accept(self, g: int) -> int:
         n = C.c_int64()
         _lib.check(_lib.lib().myfm_trainer_mh_accept(self._h, C.c_int32(g), C.byref(n)))

@@ -6,9 +6,11 @@
 #include "common.cuh"
 #include "host_data.hpp"
 #include "kernels.cuh"
+#include "mt_device.cuh"
 #include "rng.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -179,6 +181,14 @@ template <typename Real> struct Dataset : DatasetBase {
       return;
     const int lpr = pow2_ceil_clamped(K / 4.0, 1, 32);
     const int n = static_cast<int>(n_rows);
+    if (K >= 16 && X.avg_len() <= 8) { // short rows, wide factors: warp per row tile
+      const int warps = ceil_div(n, PREDICT_ROWS_PER_WARP);
+      k_predict_warp<Real><<<ceil_div(static_cast<int64_t>(warps) * 32, 256), 256, 0, stream>>>(
+          n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out, out_stride);
+      count();
+      MYFM_CUDA(cudaGetLastError());
+      return;
+    }
 #define MYFM_PREDICT(L)                                                                            \
   case L:                                                                                          \
     k_predict<Real, L><<<ceil_div(static_cast<int64_t>(n) * L, 256), 256, 0, stream>>>(            \
@@ -244,6 +254,7 @@ struct TrainerBase {
   virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
   virtual void set_profiling(bool on) = 0;
   virtual void predict_score(DatasetBase *d, double *out) = 0;
+  virtual int64_t get_variates(double *out, int64_t capacity) = 0;
   int dtype = MYFM_DTYPE_F32;
 };
 
@@ -269,7 +280,8 @@ template <typename Real> struct Trainer : TrainerBase {
   SweepPlan plan;
   std::vector<int> perm; // device row i holds the caller's row perm[i] (host_data.hpp)
   DevBuf<int> perm_dev;
-  DevBuf<int> item_col, item_lo, item_hi, seg_first, seg_count;
+  DevBuf<SweepItem> items;
+  DevBuf<int> seg_count;
   DevBuf<Real> seg_partial, seg_theta_old;
   DevBuf<Real> dense_tmp; // [N] staging for boundary copies of e / q
   std::vector<DevRelationTrain<Real>> rel_train;
@@ -291,6 +303,17 @@ template <typename Real> struct Trainer : TrainerBase {
   PinnedBuf<Real> z_pinned[2];
   cudaEvent_t z_copied[2] = {nullptr, nullptr};
   int64_t sweep_index = 0;
+  // device-side mt19937 stream (regression; mt_device.cuh): runs one sweep ahead on its own stream
+  bool device_rng = false;
+  cudaStream_t rng_stream = nullptr;
+  DevBuf<MtDeviceState> mt_state;
+  DevBuf<int> mt_error;
+  DevBuf<Real> mt_consts; // a1[G+1], a2[G+1]
+  DevBuf<Real> z_slot[2];
+  DevBuf<Real> z_raw; // (y, r2) of every bulk normal of the sweep being generated
+  cudaEvent_t z_ready[2] = {nullptr, nullptr}, z_free[2] = {nullptr, nullptr};
+  int64_t gen_index = 0;
+  const Real *z_last = nullptr;
   std::vector<Real> shapes_lw; // gamma shape per group
   Real shape_alpha = 0;
   std::vector<Real> e_host;
@@ -319,7 +342,12 @@ template <typename Real> struct Trainer : TrainerBase {
       throw CudaError("no usable CUDA device: the myfm_b200 engine has no CPU fallback.");
     MYFM_CUDA(cudaSetDevice(device));
     MYFM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    MYFM_CUDA(cudaStreamCreateWithFlags(&rng_stream, cudaStreamNonBlocking));
     for (auto &ev : z_copied)
+      MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : z_ready)
+      MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : z_free)
       MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
     // dependency levels, device row order, sweep work items (host_data.hpp)
@@ -329,6 +357,11 @@ template <typename Real> struct Trainer : TrainerBase {
       std::vector<int> level = compute_levels(Xth0, &n_levels);
       perm = primary_row_order(Xth0, level, n_levels, &primary);
       Xh = permute_rows(Xh, perm);
+      main_unit = std::all_of(Xh.val.begin(), Xh.val.end(), [](Real v) { return v == Real(1); });
+      main_row_len = Xh.n_major ? Xh.ptr[1] - Xh.ptr[0] : 0;
+      for (int64_t i = 0; i < Xh.n_major && main_row_len > 0; i++)
+        if (Xh.ptr[i + 1] - Xh.ptr[i] != main_row_len)
+          main_row_len = 0;
       HostCs<Real> Xth = host_transpose(Xh);
       plan = make_sweep_plan(Xth, level, n_levels, SWEEP_WARP_MAX, SWEEP_CHUNK);
       plan.primary_level = primary;
@@ -336,10 +369,7 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaStreamSynchronize(stream));
     }
     perm_dev.upload(perm, stream);
-    item_col.upload(plan.item_col, stream);
-    item_lo.upload(plan.item_lo, stream);
-    item_hi.upload(plan.item_hi, stream);
-    seg_first.upload(plan.seg_first, stream);
+    items.upload(plan.items, stream);
     seg_count.upload(plan.seg_count, stream);
     seg_partial.alloc(2 * static_cast<size_t>(std::max(1, plan.max_seg_items)));
     seg_theta_old.alloc(std::max(1, plan.max_seg_items));
@@ -420,9 +450,14 @@ template <typename Real> struct Trainer : TrainerBase {
   ~Trainer() override {
     if (stream)
       cudaStreamSynchronize(stream);
-    for (auto ev : z_copied)
-      if (ev)
-        cudaEventDestroy(ev);
+    if (rng_stream)
+      cudaStreamSynchronize(rng_stream);
+    for (auto *evs : {z_copied, z_ready, z_free})
+      for (int k = 0; k < 2; k++)
+        if (evs[k])
+          cudaEventDestroy(evs[k]);
+    if (rng_stream)
+      cudaStreamDestroy(rng_stream);
     if (stream)
       cudaStreamDestroy(stream);
   }
@@ -468,12 +503,87 @@ template <typename Real> struct Trainer : TrainerBase {
     hyper.upload(hh, stream);
     layout = SweepLayout::make(cfg.task_type == MYFM_TASK_REGRESSION, cfg.fit_w0, cfg.fit_linear, G,
                                K, D_all);
-    z_dev.alloc(layout.total);
-    for (auto &pb : z_pinned)
-      pb.alloc(layout.total);
+    setup_rng();
     data.predict(w.p, Vt.p, K, hv().w0, y.p, e_ptr(), 2);
     MYFM_CUDA(cudaStreamSynchronize(stream));
     sweep_index = 0;
+  }
+
+  // Chooses where the sweep variates come from.  Regression consumes the mt19937 stream in a
+  // data-independent pattern, so the stream itself moves to the device (mt_device.cuh); the
+  // host keeps it for classification (data-dependent truncated normals) and for Gamma shapes
+  // below 1 (libstdc++ takes another branch there).  MYFM_HOST_RNG=1 forces the host path.
+  void setup_rng() {
+    MYFM_CUDA(cudaStreamSynchronize(rng_stream));
+    const char *force_host = std::getenv("MYFM_HOST_RNG");
+    device_rng = cfg.task_type == MYFM_TASK_REGRESSION && shape_alpha >= 1 &&
+                 !(force_host && force_host[0] == '1');
+    for (Real sh : shapes_lw)
+      device_rng = device_rng && sh >= 1;
+    gen_index = 0, z_last = nullptr;
+    if (!device_rng) {
+      z_dev.alloc(layout.total);
+      for (auto &pb : z_pinned)
+        pb.alloc(layout.total);
+      return;
+    }
+    for (auto &zb : z_slot)
+      zb.alloc(layout.total);
+    z_raw.alloc(2 * static_cast<size_t>(layout.total));
+    // hand the generator over where create_FM left it: operator<< prints x[0..623] and p
+    std::ostringstream os;
+    os << rng.gen;
+    std::istringstream is(os.str());
+    std::vector<MtDeviceState> st(1);
+    for (int i = 0; i < MT_N; i++)
+      is >> st[0].x[i];
+    is >> st[0].p;
+    mt_state.upload(st, stream);
+    // gamma_distribution::param_type::_M_initialize (bits/random.tcc:2338-2345), shape >= 1
+    std::vector<Real> consts(2 * (G + 1));
+    for (int g = 0; g <= G; g++) {
+      const Real malpha = g < G ? shapes_lw[g] : shape_alpha;
+      const Real a1 = malpha - Real(1.0) / Real(3.0);
+      consts[g] = a1;
+      consts[G + 1 + g] = Real(1.0) / std::sqrt(Real(9.0) * a1);
+    }
+    mt_consts.upload(consts, stream);
+    mt_error.alloc(1);
+    mt_error.zero(stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  void launch_variates(int64_t index) {
+    const int slot = static_cast<int>(index & 1);
+    if (index >= 2)
+      MYFM_CUDA(cudaStreamWaitEvent(rng_stream, z_free[slot], 0));
+    const SweepLayout &L = layout;
+    MtProgram prog;
+    prog.g_alpha = L.g_alpha, prog.z_w0 = L.z_w0, prog.g_lw = L.g_lw, prog.z_mw = L.z_mw;
+    prog.z_w = L.z_w, prog.g_lV = L.g_lV, prog.z_mV = L.z_mV, prog.z_V = L.z_V;
+    prog.G = G, prog.K = K, prog.dim_all = D_all;
+    prog.a1 = mt_consts.p, prog.a2 = mt_consts.p + (G + 1);
+    k_mt_sweep_variates<Real><<<1, MT_THREADS, 0, rng_stream>>>(mt_state.p, prog, z_slot[slot].p, z_raw.p,
+                                                                mt_error.p);
+    const long long n0 = L.z_w >= 0 ? D_all : 0, n1 = static_cast<long long>(K) * D_all;
+    if (n0 + n1) {
+      k_mt_finish_normals<Real><<<ceil_div(n0 + n1, 256), 256, 0, rng_stream>>>(
+          z_raw.p, z_slot[slot].p, L.z_w >= 0 ? L.z_w : 0, n0, L.z_V, n1);
+      launched();
+    }
+    MYFM_CUDA(cudaGetLastError());
+    MYFM_CUDA(cudaEventRecord(z_ready[slot], rng_stream));
+    launched();
+  }
+
+  void check_rng_error() {
+    if (!device_rng)
+      return;
+    int err = 0;
+    MYFM_CUDA(cudaMemcpyAsync(&err, mt_error.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    if (err)
+      throw std::runtime_error("device mt19937 stream ran dry inside one draw (set MYFM_HOST_RNG=1).");
   }
 
   // Standardised variates of one sweep, in the reference's consumption order.
@@ -528,8 +638,7 @@ template <typename Real> struct Trainer : TrainerBase {
     a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
     a.partial = seg_partial.p, a.theta_old_buf = seg_theta_old.p;
     for (const SweepLevel &L : plan.levels) {
-      a.item_col = item_col.p + L.s0, a.item_lo = item_lo.p + L.s0, a.item_hi = item_hi.p + L.s0;
-      a.seg_first = seg_first.p + L.s0, a.seg_count = seg_count.p + L.s0;
+      a.item = reinterpret_cast<const int4 *>(items.p + L.s0), a.seg_count = seg_count.p + L.s0;
       a.nS = L.c0 - L.s0, a.nC = L.w0 - L.c0, a.nW = L.end - L.w0;
       const int grid = a.nS + a.nC + ceil_div(a.nW, SWEEP_WARPS);
       if (!grid)
@@ -554,9 +663,19 @@ template <typename Real> struct Trainer : TrainerBase {
     }
   }
 
+  // q_init of the main table when it is one-hot shaped (all values 1, rows of equal length)
+  bool main_unit = false;
+  int main_row_len = 0;
   void spmv(const DevCs<Real> &A, const Real *x, Real *out, bool squared, int out_stride = 1) {
     if (!A.n_major)
       return;
+    if (&A == &data.X && main_unit && main_row_len > 0 && main_row_len <= 4 && !squared) {
+      const int n = static_cast<int>(A.n_major);
+      k_spmv<Real, 1, false, true><<<ceil_div(n, 256), 256, 0, stream>>>(n, A.view(), x, out, out_stride,
+                                                                          main_row_len);
+      launched();
+      return;
+    }
     const int lpr = pow2_ceil_clamped(A.avg_len() / 4.0, 1, 32);
     const int n = static_cast<int>(A.n_major);
     const int grid = ceil_div(static_cast<int64_t>(n) * lpr, 256);
@@ -706,13 +825,22 @@ template <typename Real> struct Trainer : TrainerBase {
   // update_all (BaseFMTrainer.hpp:135-152)
   void sweep() {
     const int slot = static_cast<int>(sweep_index & 1);
-    if (sweep_index >= 2)
-      MYFM_CUDA(cudaEventSynchronize(z_copied[slot]));
-    draw_sweep_variates(z_pinned[slot].p);
-    MYFM_CUDA(cudaMemcpyAsync(z_dev.p, z_pinned[slot].p, layout.total * sizeof(Real),
-                              cudaMemcpyHostToDevice, stream));
-    MYFM_CUDA(cudaEventRecord(z_copied[slot], stream));
-    const Real *z = z_dev.p;
+    const Real *z = nullptr;
+    if (device_rng) {
+      while (gen_index <= sweep_index + 1) // this sweep's variates, and the next one's ahead of time
+        launch_variates(gen_index++);
+      MYFM_CUDA(cudaStreamWaitEvent(stream, z_ready[slot], 0));
+      z = z_slot[slot].p;
+    } else {
+      if (sweep_index >= 2)
+        MYFM_CUDA(cudaEventSynchronize(z_copied[slot]));
+      draw_sweep_variates(z_pinned[slot].p);
+      MYFM_CUDA(cudaMemcpyAsync(z_dev.p, z_pinned[slot].p, layout.total * sizeof(Real),
+                                cudaMemcpyHostToDevice, stream));
+      MYFM_CUDA(cudaEventRecord(z_copied[slot], stream));
+      z = z_dev.p;
+    }
+    z_last = z;
     HyperView<Real> h = hv();
     const SweepLayout &L = layout;
 
@@ -733,14 +861,14 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaMemsetAsync(h.w0, 0, sizeof(Real), stream));
     }
     if (G) { // update_lambda_w, update_mu_w
-      k_group_hyper<Real><<<G, 256, 0, stream>>>(G, feat_ptr.p, feat_idx.p, w.p, 0, h.mu_w, h.lambda_w,
+      k_group_hyper<Real><<<G, HYPER_THREADS, 0, stream>>>(G, feat_ptr.p, feat_idx.p, w.p, 0, h.mu_w, h.lambda_w,
                                                  z + L.g_lw, z + L.z_mw, static_cast<Real>(cfg.beta_0),
                                                  static_cast<Real>(cfg.gamma_0), static_cast<Real>(cfg.mu_0));
       launched();
     }
     update_w(L.z_w >= 0 ? z + L.z_w : nullptr);
     if (G && K) { // update_lambda_V, update_mu_V
-      k_group_hyper<Real><<<G * K, 256, 0, stream>>>(G, feat_ptr.p, feat_idx.p, V.p, D_all, h.mu_V,
+      k_group_hyper<Real><<<G * K, HYPER_THREADS, 0, stream>>>(G, feat_ptr.p, feat_idx.p, V.p, D_all, h.mu_V,
                                                      h.lambda_V, z + L.g_lV, z + L.z_mV,
                                                      static_cast<Real>(cfg.beta_0), static_cast<Real>(cfg.gamma_0),
                                                      static_cast<Real>(cfg.mu_0));
@@ -753,6 +881,8 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     if (cfg.task_type == MYFM_TASK_CLASSIFICATION)
       classification_latent();
+    if (device_rng)
+      MYFM_CUDA(cudaEventRecord(z_free[slot], stream));
     MYFM_CUDA(cudaGetLastError());
     sweep_index++;
   }
@@ -772,6 +902,17 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
     if (timer.enabled)
       timer.collect();
+    check_rng_error();
+  }
+  // the standardised variates the most recent sweep consumed (diagnostics / RNG tests)
+  int64_t get_variates(double *out, int64_t capacity) override {
+    require_fm();
+    if (!z_last || capacity < layout.total)
+      return layout.total;
+    auto h = fetch(z_last, layout.total);
+    for (int64_t i = 0; i < layout.total; i++)
+      out[i] = h[i];
+    return layout.total;
   }
   double timed_steps(int n) override {
     require_fm();
@@ -1141,6 +1282,12 @@ int myfm_trainer_set_state(myfm_trainer_t *t, const double *w0, const double *w,
   MYFM_API_BEGIN
   require(t, "trainer");
   t->impl->set_state(w0, w, V, alpha, mu_w, lambda_w, mu_V, lambda_V, e);
+  MYFM_API_END
+}
+int myfm_trainer_get_variates(myfm_trainer_t *t, double *out, int64_t capacity, int64_t *n) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(n, "n");
+  *n = t->impl->get_variates(out, capacity);
   MYFM_API_END
 }
 int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count) {

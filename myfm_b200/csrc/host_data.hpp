@@ -198,10 +198,15 @@ struct SweepLevel {
   int64_t nnz = 0;
 };
 
+struct alignas(16) SweepItem {
+  int col, lo, hi; // column and its entry range [lo, hi) in the CSC arrays
+  int first;       // S items: first chunk item of the column (level-relative)
+};
+
 struct SweepPlan {
   std::vector<SweepLevel> levels;
-  std::vector<int> item_col, item_lo, item_hi; // entry range [lo, hi) in the CSC arrays
-  std::vector<int> seg_first, seg_count;       // S items: first chunk item of the column, #chunks
+  std::vector<SweepItem> items;
+  std::vector<int> seg_count; // S items: number of chunks of the column
   int max_seg_items = 0;
   int primary_level = -1;
 };
@@ -274,25 +279,25 @@ SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level
           L.contig = false;
       }
     }
-    L.s0 = static_cast<int>(plan.item_col.size());
+    L.s0 = static_cast<int>(plan.items.size());
     auto push = [&](int j, int lo, int hi, int first, int count) {
-      plan.item_col.push_back(j), plan.item_lo.push_back(lo), plan.item_hi.push_back(hi);
-      plan.seg_first.push_back(first), plan.seg_count.push_back(count);
+      plan.items.push_back(SweepItem{j, lo, hi, first});
+      plan.seg_count.push_back(count);
     };
     size_t k = 0;
     for (; k < c.size() && len(c[k]) > chunk; k++) {
       const int j = c[k], n = (len(j) + chunk - 1) / chunk;
-      const int first = static_cast<int>(plan.item_col.size()) - L.s0; // level-relative
+      const int first = static_cast<int>(plan.items.size()) - L.s0; // level-relative
       for (int s = 0; s < n; s++)
         push(j, csc.ptr[j] + s * chunk, std::min(csc.ptr[j] + (s + 1) * chunk, csc.ptr[j + 1]), first, n);
     }
-    L.c0 = static_cast<int>(plan.item_col.size());
+    L.c0 = static_cast<int>(plan.items.size());
     for (; k < c.size() && len(c[k]) > warp_max; k++)
       push(c[k], csc.ptr[c[k]], csc.ptr[c[k] + 1], 0, 0);
-    L.w0 = static_cast<int>(plan.item_col.size());
+    L.w0 = static_cast<int>(plan.items.size());
     for (; k < c.size(); k++)
       push(c[k], csc.ptr[c[k]], csc.ptr[c[k] + 1], 0, 0);
-    L.end = static_cast<int>(plan.item_col.size());
+    L.end = static_cast<int>(plan.items.size());
     plan.max_seg_items = std::max(plan.max_seg_items, L.c0 - L.s0);
   }
   return plan;

@@ -45,16 +45,19 @@ template <typename Real> struct RelPredictPack {
 // SQUARED: out[i] = sum_p val[p]^2 * x[idx[p]]^2           (q_S;    FMTrainer.hpp:388-393)
 // LPR lanes cooperate on one row.
 // ----------------------------------------------------------------------------------------------
-template <typename Real, int LPR, bool SQUARED>
+// UNIT: every stored value is 1 (the val stream is not read).  row_len > 0: every row has exactly
+// row_len entries (the ptr stream is not read) — both hold for one-hot encoded tables.
+template <typename Real, int LPR, bool SQUARED, bool UNIT = false>
 __global__ void __launch_bounds__(256) k_spmv(int n_rows, CsView<Real> A, const Real *__restrict__ x,
-                                               Real *__restrict__ out, int out_stride) {
+                                               Real *__restrict__ out, int out_stride, int row_len = 0) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LPR, sub = tid % LPR;
   Real acc = 0;
   if (row < n_rows) {
-    const int b = A.ptr[row], en = A.ptr[row + 1];
+    const int b = row_len > 0 ? row * row_len : A.ptr[row];
+    const int en = row_len > 0 ? b + row_len : A.ptr[row + 1];
     for (int p = b + sub; p < en; p += LPR) {
-      Real v = A.val[p], xv = x[A.idx[p]];
+      Real v = UNIT ? Real(1) : A.val[p], xv = x[__ldcs(A.idx + p)];
       acc += SQUARED ? (v * v) * (xv * xv) : v * xv;
     }
   }
@@ -143,6 +146,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Forward pass for short rows: one warp walks ROWS consecutive rows; lane r owns factors r, r+32, ..
+// so every V row is read as one coalesced 128-byte line (and re-used from L1 by the following
+// rows when consecutive rows share a feature, as they do in the trainer's row order).
+constexpr int PREDICT_ROWS_PER_WARP = 16;
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_predict_warp(int n_rows, CsView<Real> X, const Real *__restrict__ w,
+                   const Real *__restrict__ Vt, int K, const Real *__restrict__ w0_ptr,
+                   RelPredictPack<Real> rels, const Real *__restrict__ y, Real *__restrict__ out,
+                   int out_stride) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const Real w0 = *w0_ptr, half = static_cast<Real>(0.5);
+  const int row0 = warp * PREDICT_ROWS_PER_WARP;
+  for (int i = 0; i < PREDICT_ROWS_PER_WARP; i++) {
+    const int row = row0 + i;
+    if (row >= n_rows)
+      return;
+    const int b = X.ptr[row], en = X.ptr[row + 1];
+    Real lin = 0, acc = 0;
+    for (int p = b + lane; p < en; p += 32)
+      lin += X.val[p] * w[X.idx[p]];
+    int srow[MAX_REL];
+#pragma unroll
+    for (int k = 0; k < MAX_REL; k++)
+      if (k < rels.n) {
+        srow[k] = rels.r[k].map[row];
+        if (lane == 0)
+          lin += rels.r[k].lin[srow[k]];
+      }
+    for (int r = lane; r < K; r += 32) {
+      Real qr = 0, sr = 0;
+      for (int p = b; p < en; p++) {
+        Real x = X.val[p], v = Vt[static_cast<size_t>(X.idx[p]) * K + r];
+        qr += x * v;
+        sr += (x * x) * (v * v);
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_REL; k++)
+        if (k < rels.n) {
+          qr += rels.r[k].q[static_cast<size_t>(srow[k]) * K + r];
+          sr += rels.r[k].qs[static_cast<size_t>(srow[k]) * K + r];
+        }
+      acc += (qr * qr) * half;
+      acc -= sr * half;
+    }
+    lin = warp_sum(lin);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      Real t = (w0 + lin) + acc;
+      out[static_cast<size_t>(row) * out_stride] = y ? t - y[row] : t;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Scalars of one sweep live in a small device array so that no step needs the host.
 // ----------------------------------------------------------------------------------------------
@@ -227,8 +284,9 @@ __global__ void __launch_bounds__(256)
 //              lin = lambda_g (gamma_0 mu_0 + sum theta)
 // feat_ptr/feat_idx: features of each group, ascending.
 // ----------------------------------------------------------------------------------------------
+constexpr int HYPER_THREADS = 1024;
 template <typename Real>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(HYPER_THREADS)
     k_group_hyper(int G, const int *__restrict__ feat_ptr, const int *__restrict__ feat_idx,
                   const Real *__restrict__ theta, int64_t theta_stride, Real *mu, Real *lambda,
                   const Real *__restrict__ g_std, const Real *__restrict__ z, Real beta_0,
@@ -239,11 +297,21 @@ __global__ void __launch_bounds__(256)
   const int b = feat_ptr[g], en = feat_ptr[g + 1];
   const Real mean = mu[g + G * v];
   Real dev2 = 0, sum = 0;
-  for (int p = b + threadIdx.x; p < en; p += blockDim.x) {
-    Real t = th[feat_idx[p]];
-    Real dev = t - mean;
-    dev2 += dev * dev;
-    sum += t;
+  // four independent gathers in flight per thread: the loop is latency-bound otherwise
+  for (int p0 = b + threadIdx.x; p0 < en; p0 += 4 * HYPER_THREADS) {
+    Real t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int p = p0 + u * HYPER_THREADS;
+      t[u] = p < en ? th[feat_idx[p]] : mean;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (p0 + u * HYPER_THREADS < en) {
+        Real dev = t[u] - mean;
+        dev2 += dev * dev;
+        sum += t[u];
+      }
   }
   dev2 = block_sum(dev2, scratch);
   sum = block_sum(sum, scratch);
@@ -289,11 +357,8 @@ constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
 template <typename Real> struct SweepArgs {
   const int *idx;       // CSC entry arrays of the main table (device row order)
   const Real *val;
-  const int *item_col;  // work items of THIS level (already offset to the level's first item)
-  const int *item_lo;
-  const int *item_hi;
-  const int *seg_first; // S items: first chunk of the column (level-relative), chunk count
-  const int *seg_count;
+  const int4 *item;     // work items of THIS level: {column, lo, hi, first chunk} (host_data.hpp: SweepItem)
+  const int *seg_count; // S items: chunks of the column
   int nS, nC, nW;
   Pair<Real> *eq;
   Real *theta;          // w, or column r of V (column-major)
@@ -394,18 +459,27 @@ __device__ __forceinline__ void store_theta(const SweepArgs<Real> &a, int j, Rea
 }
 
 // One launch per level: blocks [0, nS) chunk statistics, [nS, nS+nC) one column per CTA, the rest
-// eight columns per CTA (one per warp).
+// eight columns per CTA (one per warp).  Everything the draw needs is loaded up front so that the
+// dependent chain of a column is item -> {entries, theta, hypers} -> reduce -> draw -> scatter.
 template <typename Real, bool IS_V, bool UNIT, bool CONTIG>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_level_sweep(SweepArgs<Real> a) {
   __shared__ Real scratch[32];
   const int b = blockIdx.x;
+  const bool cta_item = b < a.nS + a.nC;
+  const int lane = threadIdx.x & 31;
+  const int w = (b - a.nS - a.nC) * SWEEP_WARPS + (threadIdx.x >> 5);
+  if (!cta_item && w >= a.nW)
+    return;
+  const int4 it = __ldg(a.item + (cta_item ? b : a.nS + a.nC + w));
+  const int j = it.x;
   const Real alpha = *a.alpha;
-  if (b < a.nS + a.nC) {
-    const int j = a.item_col[b];
-    const Real theta_old = a.theta[j];
+  const Real theta_old = a.theta[j];
+  const int g = a.group[j];
+  const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+  Real sq = 0, lin = 0;
+  if (cta_item) {
     ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
-    en.load(a, a.item_lo[b], a.item_hi[b], threadIdx.x);
-    Real sq = 0, lin = 0;
+    en.load(a, it.y, it.z, threadIdx.x);
     en.stats(theta_old, alpha, sq, lin);
     sq = block_sum(sq, scratch);
     lin = block_sum(lin, scratch);
@@ -413,33 +487,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_level_sweep(SweepArgs<Real> a
       if (threadIdx.x == 0) {
         a.partial[2 * b] = sq;
         a.partial[2 * b + 1] = lin;
-        if (a.seg_first[b] == b)
+        if (it.w == b)
           a.theta_old_buf[b] = theta_old;
       }
       return;
     }
-    const int g = a.group[j];
-    const Real theta_new =
-        column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+    const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
     if (threadIdx.x == 0)
       store_theta(a, j, theta_new);
     en.update(a, theta_old, theta_new);
   } else {
-    const int w = (b - a.nS - a.nC) * SWEEP_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (w >= a.nW)
-      return;
-    const int it = a.nS + a.nC + w;
-    const int j = a.item_col[it];
-    const Real theta_old = a.theta[j];
     ColumnEntries<Real, IS_V, UNIT, CONTIG, 32> en;
-    en.load(a, a.item_lo[it], a.item_hi[it], lane);
-    Real sq = 0, lin = 0;
+    en.load(a, it.y, it.z, lane);
     en.stats(theta_old, alpha, sq, lin);
     sq = warp_sum(sq);
     lin = warp_sum(lin);
-    const int g = a.group[j];
-    const Real theta_new =
-        column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
+    const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
     if (lane == 0)
       store_theta(a, j, theta_new);
     en.update(a, theta_old, theta_new);
@@ -452,8 +515,14 @@ template <typename Real, bool IS_V, bool UNIT, bool CONTIG>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_level_seg_update(SweepArgs<Real> a) {
   __shared__ Real bcast[2];
   const int b = blockIdx.x;
-  const int j = a.item_col[b];
-  const int first = a.seg_first[b], last = first + a.seg_count[b];
+  const int4 it = __ldg(a.item + b);
+  const int j = it.x;
+  const int first = it.w, last = first + a.seg_count[b];
+  const int g = a.group[j];
+  const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j], alpha = *a.alpha;
+  const Real theta_old = a.theta_old_buf[first];
+  ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
+  en.load(a, it.y, it.z, threadIdx.x);
   if (threadIdx.x < 32) {
     Real sq = 0, lin = 0;
     for (int i = first + threadIdx.x; i < last; i += 32) {
@@ -465,13 +534,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_level_seg_update(SweepArgs<Re
     if (threadIdx.x == 0)
       bcast[0] = sq, bcast[1] = lin;
   }
-  ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
-  en.load(a, a.item_lo[b], a.item_hi[b], threadIdx.x);
   __syncthreads();
-  const Real theta_old = a.theta_old_buf[first];
-  const int g = a.group[j];
-  const Real theta_new = column_draw<Real, IS_V>(bcast[0], bcast[1], theta_old, *a.alpha,
-                                                 a.lambda[g], a.mu[g], a.z[j]);
+  const Real theta_new = column_draw<Real, IS_V>(bcast[0], bcast[1], theta_old, alpha, lam, mu, z);
   if (b == first && threadIdx.x == 0)
     store_theta(a, j, theta_new);
   en.update(a, theta_old, theta_new);
