@@ -181,10 +181,15 @@ template <typename Real> struct Dataset : DatasetBase {
       return;
     const int lpr = pow2_ceil_clamped(K / 4.0, 1, 32);
     const int n = static_cast<int>(n_rows);
-    if (K >= 16 && X.avg_len() <= 8) { // short rows, wide factors: warp per row tile
+    if (K >= 16 && K <= 64 && X.avg_len() <= 16) { // short rows, wide factors: warp per row tile
       const int warps = ceil_div(n, PREDICT_ROWS_PER_WARP);
-      k_predict_warp<Real><<<ceil_div(static_cast<int64_t>(warps) * 32, 256), 256, 0, stream>>>(
-          n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out, out_stride);
+      const int grid = ceil_div(static_cast<int64_t>(warps) * 32, 256);
+      if (pack.n)
+        k_predict_warp<Real, true><<<grid, 256, 0, stream>>>(n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out,
+                                                             out_stride);
+      else
+        k_predict_warp<Real, false><<<grid, 256, 0, stream>>>(n, X.view(), w_dev, Vt_dev, K, w0_dev, pack, y, out,
+                                                              out_stride);
       count();
       MYFM_CUDA(cudaGetLastError());
       return;

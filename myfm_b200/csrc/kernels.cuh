@@ -146,11 +146,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Forward pass for short rows: one warp walks ROWS consecutive rows; lane r owns factors r, r+32, ..
-// so every V row is read as one coalesced 128-byte line (and re-used from L1 by the following
-// rows when consecutive rows share a feature, as they do in the trainer's row order).
+// Forward pass for short rows: one warp walks PREDICT_ROWS_PER_WARP consecutive rows.  The lanes
+// first load the row's entries (coalesced), then every lane owns factors lane, lane+32, .. and
+// reads each V row as one coalesced line (re-used from L1 when consecutive rows share a feature,
+// as they do in the trainer's row order).  One shuffle reduction per row.
 constexpr int PREDICT_ROWS_PER_WARP = 16;
-template <typename Real>
+template <typename Real, bool HAS_REL>
 __global__ void __launch_bounds__(256)
     k_predict_warp(int n_rows, CsView<Real> X, const Real *__restrict__ w,
                    const Real *__restrict__ Vt, int K, const Real *__restrict__ w0_ptr,
@@ -159,42 +160,68 @@ __global__ void __launch_bounds__(256)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const Real w0 = *w0_ptr, half = static_cast<Real>(0.5);
   const int row0 = warp * PREDICT_ROWS_PER_WARP;
-  for (int i = 0; i < PREDICT_ROWS_PER_WARP; i++) {
+  if (row0 >= n_rows)
+    return;
+  const int n_mine = min(PREDICT_ROWS_PER_WARP, n_rows - row0);
+  // row pointers of the tile: lane i holds ptr[row0 + i]
+  const int my_ptr = lane <= n_mine ? X.ptr[row0 + lane] : 0;
+  for (int i = 0; i < n_mine; i++) {
     const int row = row0 + i;
-    if (row >= n_rows)
-      return;
-    const int b = X.ptr[row], en = X.ptr[row + 1];
-    Real lin = 0, acc = 0;
-    for (int p = b + lane; p < en; p += 32)
-      lin += X.val[p] * w[X.idx[p]];
+    const int b = __shfl_sync(FULL_MASK, my_ptr, i), en = __shfl_sync(FULL_MASK, my_ptr, i + 1);
+    Real total = 0; // per-lane share of lin + 1/2 sum_r (q_r^2 - s_r)
+    Real qr[2] = {0, 0}, sr[2] = {0, 0}; // factors lane and lane + 32; further ones below
+    for (int c = b; c < en; c += 32) {
+      const int p = c + lane;
+      int j = 0;
+      Real x = 0;
+      if (p < en) {
+        j = __ldcs(X.idx + p), x = __ldcs(X.val + p);
+        total += x * w[j];
+      }
+      const int m = min(32, en - c);
+      for (int k = 0; k < m; k++) {
+        const int jk = __shfl_sync(FULL_MASK, j, k);
+        const Real xk = __shfl_sync(FULL_MASK, x, k);
+        const Real *vrow = Vt + static_cast<size_t>(jk) * K;
+        if (lane < K) {
+          Real v = vrow[lane];
+          qr[0] += xk * v, sr[0] += (xk * xk) * (v * v);
+        }
+        if (lane + 32 < K) {
+          Real v = vrow[lane + 32];
+          qr[1] += xk * v, sr[1] += (xk * xk) * (v * v);
+        }
+      }
+    }
     int srow[MAX_REL];
-#pragma unroll
-    for (int k = 0; k < MAX_REL; k++)
-      if (k < rels.n) {
-        srow[k] = rels.r[k].map[row];
-        if (lane == 0)
-          lin += rels.r[k].lin[srow[k]];
-      }
-    for (int r = lane; r < K; r += 32) {
-      Real qr = 0, sr = 0;
-      for (int p = b; p < en; p++) {
-        Real x = X.val[p], v = Vt[static_cast<size_t>(X.idx[p]) * K + r];
-        qr += x * v;
-        sr += (x * x) * (v * v);
-      }
+    if (HAS_REL) {
 #pragma unroll
       for (int k = 0; k < MAX_REL; k++)
         if (k < rels.n) {
-          qr += rels.r[k].q[static_cast<size_t>(srow[k]) * K + r];
-          sr += rels.r[k].qs[static_cast<size_t>(srow[k]) * K + r];
+          srow[k] = rels.r[k].map[row];
+          if (lane == 0)
+            total += rels.r[k].lin[srow[k]];
         }
-      acc += (qr * qr) * half;
-      acc -= sr * half;
     }
-    lin = warp_sum(lin);
-    acc = warp_sum(acc);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = lane + 32 * u;
+      if (r < K) {
+        if (HAS_REL) {
+#pragma unroll
+          for (int k = 0; k < MAX_REL; k++)
+            if (k < rels.n) {
+              qr[u] += rels.r[k].q[static_cast<size_t>(srow[k]) * K + r];
+              sr[u] += rels.r[k].qs[static_cast<size_t>(srow[k]) * K + r];
+            }
+        }
+        total += (qr[u] * qr[u]) * half;
+        total -= sr[u] * half;
+      }
+    }
+    total = warp_sum(total);
     if (lane == 0) {
-      Real t = (w0 + lin) + acc;
+      Real t = w0 + total;
       out[static_cast<size_t>(row) * out_stride] = y ? t - y[row] : t;
     }
   }
@@ -389,26 +416,34 @@ __device__ __forceinline__ Real column_draw(Real sq, Real lin, Real theta_old, R
   return (lin / sq) + z / sqrt(sq);
 }
 
-// The entries one thread owns: t, t + NT, t + 2 NT, ... of [lo, hi).
+// The entries one thread owns: t, t + NT, t + 2 NT, ... of [lo, hi).  Only the first
+// ceil((hi - lo) / NT) slots are touched (uniform across the warp / CTA).
 template <typename Real, bool IS_V, bool UNIT, bool CONTIG, int NT> struct ColumnEntries {
   int i[SWEEP_R];
   Real x[SWEEP_R], e[SWEEP_R], q[SWEEP_R];
+  int n_slots;
 
   __device__ __forceinline__ void load(const SweepArgs<Real> &a, int lo, int hi, int t) {
+    n_slots = (hi - lo + NT - 1) / NT;
     int first = 0;
     if (CONTIG)
       first = lo < hi ? a.idx[lo] : 0;
 #pragma unroll
     for (int s = 0; s < SWEEP_R; s++) {
-      const int p = lo + t + s * NT;
-      const bool ok = p < hi;
-      i[s] = ok ? (CONTIG ? first + (p - lo) : __ldcs(a.idx + p)) : -1;
-      x[s] = UNIT ? Real(1) : (ok ? __ldcs(a.val + p) : Real(0));
+      i[s] = -1, x[s] = Real(UNIT ? 1 : 0);
+      if (s < n_slots) {
+        const int p = lo + t + s * NT;
+        if (p < hi) {
+          i[s] = CONTIG ? first + (p - lo) : __ldcs(a.idx + p);
+          if (!UNIT)
+            x[s] = __ldcs(a.val + p);
+        }
+      }
     }
 #pragma unroll
     for (int s = 0; s < SWEEP_R; s++) {
       e[s] = 0, q[s] = 0;
-      if (i[s] >= 0) {
+      if (s < n_slots && i[s] >= 0) {
         const Pair<Real> v = __ldcg(a.eq + i[s]);
         e[s] = v.x, q[s] = v.y;
       }
@@ -418,7 +453,7 @@ template <typename Real, bool IS_V, bool UNIT, bool CONTIG, int NT> struct Colum
   __device__ __forceinline__ void stats(Real theta_old, Real alpha, Real &sq, Real &lin) const {
 #pragma unroll
     for (int s = 0; s < SWEEP_R; s++)
-      if (i[s] >= 0) {
+      if (s < n_slots && i[s] >= 0) {
         if (IS_V) {
           Real h = x[s] * (q[s] - x[s] * theta_old);
           sq += h * h;
@@ -435,7 +470,7 @@ template <typename Real, bool IS_V, bool UNIT, bool CONTIG, int NT> struct Colum
                                          Real theta_new) const {
 #pragma unroll
     for (int s = 0; s < SWEEP_R; s++)
-      if (i[s] >= 0) {
+      if (s < n_slots && i[s] >= 0) {
         Pair<Real> v;
         if (IS_V) {
           Real h = x[s] * (q[s] - x[s] * theta_old);
@@ -462,7 +497,7 @@ __device__ __forceinline__ void store_theta(const SweepArgs<Real> &a, int j, Rea
 // eight columns per CTA (one per warp).  Everything the draw needs is loaded up front so that the
 // dependent chain of a column is item -> {entries, theta, hypers} -> reduce -> draw -> scatter.
 template <typename Real, bool IS_V, bool UNIT, bool CONTIG>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_level_sweep(SweepArgs<Real> a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, sizeof(Real) == 4 ? 5 : 3) k_level_sweep(SweepArgs<Real> a) {
   __shared__ Real scratch[32];
   const int b = blockIdx.x;
   const bool cta_item = b < a.nS + a.nC;

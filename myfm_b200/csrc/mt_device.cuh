@@ -70,14 +70,14 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t z) {
 
 // generate_canonical<float, 24>: one word (bits/random.tcc:3349-3385)
 __device__ __forceinline__ float mt_canonical(const uint32_t *w, float) {
-  float r = __uint2float_rn(w[0]) / 4294967296.0f;
+  float r = __uint2float_rn(w[0]) * 2.3283064365386963e-10f; // / 2^32, exact
   return r >= 1.0f ? 0.99999994f : r; // nextafter(1, 0)
 }
 // generate_canonical<double, 53>: two words, low word first
 __device__ __forceinline__ double mt_canonical(const uint32_t *w, double) {
   double sum = static_cast<double>(w[0]);
   sum += static_cast<double>(w[1]) * 4294967296.0;
-  double r = sum / 18446744073709551616.0;
+  double r = sum * 5.42101086242752217e-20; // / 2^64, exact
   return r >= 1.0 ? 0.99999999999999988898 : r;
 }
 __device__ __forceinline__ float mt_log(float x) { return static_cast<float>(log(static_cast<double>(x))); }
@@ -100,49 +100,45 @@ template <typename Real> __device__ __forceinline__ Real mt_polar_mult(Real r2) 
 template <typename Real> struct MtCta {
   uint32_t *cur, *prev; // [624] each: untempered state of the last two generated blocks
   uint32_t *buf;        // [MT_BUF_WORDS] tempered words not yet consumed: buf[head .. head+avail)
-  int *ctl;             // [0] head, [1] avail, [2] size of the last appended block, [3] error, [4] scratch
+  int *ctl;             // [0] head, [1] avail (scalar-phase hand-off), [3] error, [4..5] round scratch
   int *warp_tot;        // [32]
-
-  __device__ int head() const { return ctl[0]; }
-  __device__ int avail() const { return ctl[1]; }
+  // Uniform per-thread copies: every thread tracks the buffer window itself, so appending a block
+  // needs no bookkeeping barrier.  Thread 0 alone moves them during a scalar draw and publishes
+  // the result through ctl[0..1].
+  int head = 0, avail = 0, last = 0; // last = size of the most recently appended block
 
   // Moves the unconsumed words to the front of the buffer.  All threads; ends with a barrier.
   __device__ void compact() {
-    const int h = ctl[0], n = ctl[1];
-    __syncthreads();
-    if (h > 0) {
-      // forward copy in chunks of blockDim: a chunk is read completely before it is written
-      for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        uint32_t v = 0;
-        if (i < n)
-          v = buf[h + i];
-        __syncthreads();
-        if (i < n)
-          buf[i] = v;
-        __syncthreads();
-      }
-      if (threadIdx.x == 0)
-        ctl[0] = 0;
+    if (head == 0)
+      return;
+    const int h = head, n = avail;
+    // forward copy in chunks of blockDim: a chunk is read completely before it is written
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      uint32_t v = 0;
+      if (i < n)
+        v = buf[h + i];
+      __syncthreads();
+      if (i < n)
+        buf[i] = v;
     }
+    head = 0;
     __syncthreads();
   }
 
-  // Appends one block of tempered words: at kernel start the rest of the current state block,
-  // afterwards a freshly regenerated block.  Caller guarantees head == 0 and room for 624 words.
+  // Appends the rest of the state block the kernel starts with.
   __device__ void append_initial(uint32_t p) {
     const int n = MT_N - static_cast<int>(p);
     for (int i = threadIdx.x; i < n; i += blockDim.x)
-      buf[ctl[0] + ctl[1] + i] = mt_temper(cur[p + i]);
-    __syncthreads();
-    if (threadIdx.x == 0)
-      ctl[1] += n, ctl[2] = n;
+      buf[head + avail + i] = mt_temper(cur[p + i]);
+    avail += n, last = n;
     __syncthreads();
   }
+  // Regenerates the next block of 624 words (three barriers) and appends its tempered words.
   __device__ void append_block() {
     uint32_t *x = cur, *y = prev; // y becomes the new block; the roles swap at the end
     const int t = threadIdx.x;
-    uint32_t *out = buf + ctl[0] + ctl[1];
+    uint32_t *out = buf + head + avail;
     if (t < MT_N - MT_M) { // [0, 227)
       uint32_t v = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
       y[t] = v, out[t] = mt_temper(v);
@@ -165,35 +161,33 @@ template <typename Real> struct MtCta {
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0)
-      ctl[1] += MT_N, ctl[2] = MT_N;
-    cur = y, prev = x; // every thread keeps its own (identical) copy of the two pointers
-    __syncthreads();
+    avail += MT_N, last = MT_N;
+    cur = y, prev = x;
   }
   // Makes at least `need` words available (need <= 624).  Uniform across the CTA.
   __device__ void ensure(int need) {
-    if (ctl[1] >= need)
+    if (avail >= need)
       return;
-    if (ctl[0] + ctl[1] + MT_N > MT_BUF_WORDS)
+    if (head + avail + MT_N > MT_BUF_WORDS)
       compact();
     append_block();
   }
   // Fills the buffer to capacity (bulk phase).
   __device__ void fill() {
     compact();
-    while (ctl[1] + MT_N <= MT_BUF_WORDS)
+    while (avail + MT_N <= MT_BUF_WORDS)
       append_block();
   }
 
   // ---- scalar draws (thread 0 only; at least 624 words available) ------------------------------
   __device__ bool take(int n, const uint32_t *&w) {
-    if (ctl[1] < n) {
+    if (avail < n) {
       ctl[3] = 1; // ran dry inside one draw: p < 1e-90, reported to the host
       w = buf;
       return false;
     }
-    w = buf + ctl[0];
-    ctl[0] += n, ctl[1] -= n;
+    w = buf + head;
+    head += n, avail -= n;
     return true;
   }
   struct Normal { // std::normal_distribution<Real>(0, 1)
@@ -239,6 +233,18 @@ template <typename Real> struct MtCta {
     }
     return a1 * v;
   }
+  // One scalar draw by thread 0 (kind 0 = fresh normal, 1 = gamma); all threads call.
+  __device__ void scalar(int kind, Real a1, Real a2, Real *dst) {
+    ensure(MT_N);
+    if (threadIdx.x == 0) {
+      Normal nd;
+      *dst = kind == 0 ? normal(nd) : gamma(a1, a2);
+      ctl[0] = head, ctl[1] = avail;
+    }
+    __syncthreads();
+    head = ctl[0], avail = ctl[1];
+    __syncthreads(); // ctl is rewritten by the next draw
+  }
 
   // ---- bulk: `count` fresh normals in a row -----------------------------------------------------
   // Writes, for the k-th accepted polar attempt, the pair (y, r2) to raw[k]; the transform
@@ -253,13 +259,15 @@ template <typename Real> struct MtCta {
     constexpr int KMAX = ((MAX_ATTEMPTS + NWARPS - 1) / NWARPS + 31) / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    int round = 0;
     while (count > 0) {
       if (count >= MAX_ATTEMPTS)
         fill(); // every attempt of the buffer will be consumed
       else
         ensure(WPA); // tail: one block at a time, so that the state can be handed over exactly
-      const int A = ctl[1] / WPA;
-      const int h = ctl[0];
+      int *used_attempts = ctl + 4 + (round++ & 1);
+      const int A = avail / WPA;
+      const int h = head;
       const int S = (A + NWARPS - 1) / NWARPS;
       const int wa0 = min(A, wid * S), wa1 = min(A, wa0 + S);
       unsigned masks[KMAX];
@@ -279,7 +287,7 @@ template <typename Real> struct MtCta {
       if (lane == 0)
         warp_tot[wid] = cnt;
       if (threadIdx.x == 0)
-        ctl[4] = A; // attempts consumed (lowered below when the segment ends inside this round)
+        *used_attempts = A; // lowered below when the segment ends inside this round
       __syncthreads();
       int off = 0, total = 0;
 #pragma unroll
@@ -301,17 +309,14 @@ template <typename Real> struct MtCta {
             raw[2 * static_cast<long long>(idx) + 1] = r2s[k];
           }
           if (completes && idx + 1 == want)
-            ctl[4] = wa0 + k * 32 + lane + 1; // the attempt that produced the segment's last normal
+            *used_attempts = wa0 + k * 32 + lane + 1; // produced the segment's last normal
         }
         off += __popc(m);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        const int used = ctl[4] * WPA;
-        ctl[0] += used, ctl[1] -= used;
-      }
+      const int used = *used_attempts * WPA;
+      head += used, avail -= used;
       raw += 2 * want, count -= want;
-      __syncthreads();
     }
   }
 };
@@ -351,35 +356,26 @@ __global__ void __launch_bounds__(MT_THREADS)
 
   const Real *a1 = static_cast<const Real *>(prog.a1), *a2 = static_cast<const Real *>(prog.a2);
   const int G = prog.G, K = prog.K;
-  // scalar draw number `k` of a segment: kind 0 = fresh normal, 1 = gamma with constants index ci
-  auto scalar = [&](int kind, int ci, long long dst) {
-    c.ensure(MT_N);
-    if (threadIdx.x == 0) {
-      typename MtCta<Real>::Normal nd;
-      out[dst] = kind == 0 ? c.normal(nd) : c.gamma(a1[ci], a2[ci]);
-    }
-    __syncthreads();
-  };
   if (prog.g_alpha >= 0)
-    scalar(1, G, prog.g_alpha);
+    c.scalar(1, a1[G], a2[G], out + prog.g_alpha);
   if (prog.z_w0 >= 0)
-    scalar(0, 0, prog.z_w0);
+    c.scalar(0, 0, 0, out + prog.z_w0);
   for (int g = 0; g < G; g++)
-    scalar(1, g, prog.g_lw + g);
+    c.scalar(1, a1[g], a2[g], out + prog.g_lw + g);
   for (int g = 0; g < G; g++)
-    scalar(0, 0, prog.z_mw + g);
+    c.scalar(0, 0, 0, out + prog.z_mw + g);
   if (prog.z_w >= 0)
     c.bulk_normals(raw + 2 * prog.z_w, prog.dim_all);
   for (int r = 0; r < K; r++)
     for (int g = 0; g < G; g++)
-      scalar(1, g, prog.g_lV + static_cast<long long>(r) * G + g);
+      c.scalar(1, a1[g], a2[g], out + prog.g_lV + static_cast<long long>(r) * G + g);
   for (long long i = 0; i < static_cast<long long>(K) * G; i++)
-    scalar(0, 0, prog.z_mV + i);
+    c.scalar(0, 0, 0, out + prog.z_mV + i);
   c.bulk_normals(raw + 2 * prog.z_V, static_cast<long long>(K) * prog.dim_all);
 
   // hand the generator over: the unconsumed words are the tail of [prev block][cur block]
   __syncthreads();
-  const int left = s_ctl[1], last = s_ctl[2];
+  const int left = c.avail, last = c.last;
   const uint32_t *src = left <= last ? c.cur : c.prev;
   const uint32_t p = left <= last ? MT_N - left : 2 * MT_N - left;
   for (int i = threadIdx.x; i < MT_N; i += blockDim.x)
