@@ -7,6 +7,7 @@
 #include "host_data.hpp"
 #include "kernels.cuh"
 #include "mt_device.cuh"
+#include "oprobit.cuh"
 #include "rng.hpp"
 
 #include <cmath>
@@ -322,6 +323,16 @@ template <typename Real> struct Trainer : TrainerBase {
   std::vector<Real> shapes_lw; // gamma shape per group
   Real shape_alpha = 0;
   std::vector<Real> e_host;
+  // ordered probit: one cut-point sampler per cut-point group (FMTrainer.hpp:101-116, 513-521)
+  struct CutGroup {
+    int n_class = 0;
+    std::vector<int64_t> rows;         // caller's row ids in the order given (the latent draws follow it)
+    DevBuf<int> class_ptr, class_rows; // device rows of the group, grouped by label
+    std::unique_ptr<CutpointSampler<Real>> sampler;
+    std::vector<Real> cutpoints;
+  };
+  std::vector<CutGroup> cut_groups;
+  DevBuf<Real> op_gamma, op_partial, op_sums;
 
   Trainer(const myfm_csr_t &X_api, int n_rel, const myfm_relation_t *relations, const double *y_api,
           int64_t n_y, int seed, const myfm_config_t &cfg_api, const myfm_engine_options_t &o)
@@ -331,8 +342,6 @@ template <typename Real> struct Trainer : TrainerBase {
       throw std::runtime_error("rng=philox is not available in this build; use rng=mt19937.");
     if (o.world_size > 1)
       throw std::runtime_error("row-sharded multi-GPU training is not available in this build.");
-    if (cfg.task_type == MYFM_TASK_ORDERED)
-      throw std::runtime_error("ordered probit is not available in this build.");
     HostCs<Real> Xh = host_from_api<Real>(X_api, "X");
     if (Xh.n_major != n_y) { // BaseFMTrainer.hpp:69-76
       std::ostringstream ss;
@@ -436,6 +445,26 @@ template <typename Real> struct Trainer : TrainerBase {
     eq_buf.alloc(2 * static_cast<size_t>(N));
     eq_buf.zero(stream);
     dense_tmp.alloc(N);
+    if (cfg.task_type == MYFM_TASK_ORDERED) { // BaseFMTrainer.hpp:79-104
+      std::vector<char> seen(N, 0);
+      for (auto &grp : cfg.cutpoint_groups)
+        for (int64_t k : grp.second) {
+          if (k < 0 || k >= N)
+            throw std::invalid_argument("out of range for cutpoint group config.");
+          if (seen[k]) {
+            std::ostringstream ss;
+            ss << "index " << k << " overlapping in cutpoint config.";
+            throw std::invalid_argument(ss.str());
+          }
+          seen[k] = 1;
+        }
+      for (int64_t i = 0; i < N; i++)
+        if (!seen[i]) {
+          std::ostringstream ss;
+          ss << "cutpoint group not specified for " << i << ".";
+          throw std::invalid_argument(ss.str());
+        }
+    }
     group.upload(cfg.group_index, stream);
     feat_ptr.upload(cfg.feat_ptr, stream);
     feat_idx.upload(cfg.feat_idx, stream);
@@ -509,7 +538,10 @@ template <typename Real> struct Trainer : TrainerBase {
     layout = SweepLayout::make(cfg.task_type == MYFM_TASK_REGRESSION, cfg.fit_w0, cfg.fit_linear, G,
                                K, D_all);
     setup_rng();
-    data.predict(w.p, Vt.p, K, hv().w0, y.p, e_ptr(), 2);
+    const bool ordered = cfg.task_type == MYFM_TASK_ORDERED;
+    data.predict(w.p, Vt.p, K, hv().w0, ordered ? nullptr : y.p, e_ptr(), 2);
+    if (ordered)
+      ordered_update(true);
     MYFM_CUDA(cudaStreamSynchronize(stream));
     sweep_index = 0;
   }
@@ -809,6 +841,108 @@ template <typename Real> struct Trainer : TrainerBase {
     import_component(0, e_host.data());
   }
 
+  // Builds the samplers of the cut-point groups (OProbitSampler.hpp:25-49: label checks).
+  void build_cut_groups() {
+    cut_groups.clear();
+    cut_groups.reserve(cfg.cutpoint_groups.size()); // the samplers' callbacks keep pointers into it
+    std::vector<int> inv(N);
+    for (int64_t i = 0; i < N; i++)
+      inv[perm[i]] = static_cast<int>(i);
+    int max_class = 1;
+    for (auto &grp : cfg.cutpoint_groups) {
+      cut_groups.emplace_back();
+      CutGroup &cg = cut_groups.back();
+      cg.n_class = grp.first;
+      if (cg.n_class < 2)
+        throw std::invalid_argument("a cutpoint group needs at least two classes.");
+      cg.rows = grp.second;
+      std::vector<int> class_ptr(cg.n_class + 1, 0), class_rows(cg.rows.size());
+      for (int64_t i : cg.rows) {
+        const Real yi = y_host[i];
+        const int label = static_cast<int>(yi);
+        if (std::abs(label - yi) > 1e-3)
+          throw std::invalid_argument("y has a floating-point element.");
+        if (label < 0)
+          throw std::invalid_argument("y has a negative element.");
+        if (label >= cg.n_class) {
+          std::ostringstream ss;
+          ss << "y[ " << i << "] is greater than " << (cg.n_class - 1) << ".";
+          throw std::invalid_argument(ss.str());
+        }
+        class_ptr[label + 1]++;
+      }
+      for (int c = 0; c < cg.n_class; c++)
+        class_ptr[c + 1] += class_ptr[c];
+      std::vector<int> cur(class_ptr.begin(), class_ptr.end() - 1);
+      for (int64_t i : cg.rows)
+        class_rows[cur[static_cast<int>(y_host[i])]++] = inv[i];
+      cg.class_ptr.upload(class_ptr, stream);
+      cg.class_rows.upload(class_rows, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+      cg.cutpoints.assign(cg.n_class - 1, Real(0));
+      CutGroup *self = &cg;
+      cg.sampler = std::make_unique<CutpointSampler<Real>>(
+          cg.n_class, static_cast<Real>(cfg.reg_0), static_cast<Real>(cfg.nu_oprobit),
+          [this, self](const std::vector<Real> &gamma, std::vector<Real> &sums) {
+            cutpoint_row_sums(*self, gamma, sums);
+          });
+      max_class = std::max(max_class, cg.n_class);
+    }
+    op_gamma.alloc(max_class);
+    op_partial.alloc(static_cast<size_t>(max_class) * OP_BLOCKS_PER_CLASS * OP_TERMS);
+    op_sums.alloc(static_cast<size_t>(max_class) * OP_TERMS);
+  }
+
+  // Label-wise sums of the cut-point log-posterior terms over the group's rows, on the device;
+  // e holds the current scores while the cut-points are being sampled (FMTrainer.hpp:494,513-521).
+  void cutpoint_row_sums(CutGroup &cg, const std::vector<Real> &gamma, std::vector<Real> &sums) {
+    const int Kc = cg.n_class;
+    op_gamma.upload(gamma.data(), gamma.size(), stream);
+    k_oprobit_terms<Real><<<Kc * OP_BLOCKS_PER_CLASS, OP_THREADS, 0, stream>>>(
+        Kc, cg.class_ptr.p, cg.class_rows.p, e_ptr(), 2, op_gamma.p, op_partial.p);
+    k_oprobit_finish<Real><<<ceil_div(Kc * OP_TERMS, 128), 128, 0, stream>>>(Kc, op_partial.p, op_sums.p);
+    launched(2);
+    MYFM_CUDA(cudaGetLastError());
+    sums.resize(static_cast<size_t>(Kc) * OP_TERMS);
+    op_sums.download(sums.data(), sums.size(), stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // ORDERED part of initialize_e (start = true, FMTrainer.hpp:101-116) and of update_e
+  // (:513-521): cut-point move, then the latent z of every row from a normal truncated to the
+  // label's interval (OProbitSampler.hpp:238-272); e <- score - z.  The truncated normals consume
+  // the mt19937 stream row by row, so they are drawn on the host.
+  void ordered_update(bool start) {
+    if (start)
+      build_cut_groups();
+    e_host.resize(N);
+    export_component(0, e_host.data());
+    for (CutGroup &cg : cut_groups) {
+      if (start)
+        cg.sampler->start();
+      else
+        cg.sampler->step(rng.gen);
+      cg.cutpoints = cg.sampler->gamma_now;
+      const std::vector<Real> &gamma = cg.cutpoints;
+      const int Kc = cg.n_class;
+      const Real deviation = 1;
+      for (int64_t i : cg.rows) {
+        const int label = static_cast<int>(y_host[i]);
+        const Real pred = e_host[i];
+        Real z;
+        if (label == 0)
+          z = deviation * rng.tn_right((gamma[label] - pred) / deviation) + pred;
+        else if (label == Kc - 1)
+          z = deviation * rng.tn_left((gamma[Kc - 2] - pred) / deviation) + pred;
+        else
+          z = deviation * rng.tn_twoside((gamma[label - 1] - pred) / deviation,
+                                         (gamma[label] - pred) / deviation) + pred;
+        e_host[i] -= z;
+      }
+    }
+    import_component(0, e_host.data());
+  }
+
   // eq component (0 = e, 1 = q) <-> a dense host vector in the caller's row order
   void export_component(int comp, Real *host) {
     if (!N)
@@ -886,6 +1020,8 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     if (cfg.task_type == MYFM_TASK_CLASSIFICATION)
       classification_latent();
+    if (cfg.task_type == MYFM_TASK_ORDERED)
+      ordered_update(false);
     if (device_rng)
       MYFM_CUDA(cudaEventRecord(z_free[slot], stream));
     MYFM_CUDA(cudaGetLastError());
@@ -959,7 +1095,12 @@ template <typename Real> struct Trainer : TrainerBase {
     for (size_t i = 0; i < Vh.size(); i++)
       V_out[i] = Vh[i];
   }
-  void get_cutpoints(int, double *) override { throw std::runtime_error("No cutpoint available for this FM."); }
+  void get_cutpoints(int g, double *out) override {
+    if (g < 0 || g >= static_cast<int>(cut_groups.size()))
+      throw std::runtime_error("No cutpoint available for this FM.");
+    for (size_t c = 0; c < cut_groups[g].cutpoints.size(); c++)
+      out[c] = cut_groups[g].cutpoints[c];
+  }
   void get_hyper(double *alpha, double *mu_w, double *lambda_w, double *mu_V, double *lambda_V) override {
     require_fm();
     auto hh = fetch(hyper.p, hyper_size());
@@ -984,7 +1125,11 @@ template <typename Real> struct Trainer : TrainerBase {
     for (int64_t i = 0; i < N; i++)
       out[i] = h[i];
   }
-  int64_t mh_accept(int) override { return 0; }
+  int64_t mh_accept(int g) override {
+    if (g < 0 || g >= static_cast<int>(cut_groups.size()))
+      throw std::invalid_argument("cutpoint group index out of range.");
+    return cut_groups[g].sampler->accept_count;
+  }
 
   // Overwrites parts of the chain state (NULL = keep).  Layouts as in the getters.
   void set_state(const double *w0_in, const double *w_in, const double *V_in, const double *alpha_in,

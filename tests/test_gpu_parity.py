@@ -282,3 +282,76 @@ def test_device_mt19937_stream_matches_libstdcxx(engine, dtype, rank, monkeypatc
     for it, (a, b) in enumerate(zip(dev, host)):
         assert a.shape == b.shape
         np.testing.assert_allclose(a, b, rtol=tol, atol=0, err_msg=f"sweep {it}")
+
+
+def ordinal_1dim(n=1000):
+    """The reference's ordered-probit fixture (tests/oprobit/test_oprobit_1dim.py:11-19)."""
+    cps = np.asarray([0.0, 0.5, 1.5])
+    rns = np.random.RandomState(0)
+    X = rns.normal(0, 2, size=n)
+    score = X * 0.5 + rns.randn(n)
+    y = np.zeros(n)
+    for cp in cps:
+        y += (score > cp).astype(np.int64)
+    return sps.csr_matrix(X[:, None]), y
+
+
+def assert_ordered_close(trainer, chain, dtype, what, free_running=True):
+    assert_state_close(trainer, chain, dtype, what, free_running=free_running)
+    tol = FREE_RUNNING_F32 if dtype == "f32" else None
+    close(trainer.get_fm()[3][0], chain.cutpoints()[0], dtype, f"cutpoints {what}", tol)
+    assert trainer.mh_accept(0) == chain.mh_accept(0), what
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_ordered_probit_chain_1dim(engine, oracle, dtype):
+    """Reference fixture, rank 0, 4 classes: cut-point Newton + MH on device-reduced sums, latent
+    z from the shared mt19937 stream; compared with the oracle after init and every sweep."""
+    X, y = ordinal_1dim()
+    trainer, chain = make_pair(engine, oracle, X, y, 0, dtype, task="ordered", fit_w0=False)
+    assert_ordered_close(trainer, chain, dtype, "after init")
+    for it in range(8 if dtype == "f64" else 3):
+        trainer.step(1)
+        chain.step()
+        assert_ordered_close(trainer, chain, dtype, f"after sweep {it}")
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_ordered_probit_chain_factorized(engine, oracle, dtype):
+    """Ordered probit on MovieLens-shaped data (rank 4, 5 ordinal classes, two groups)."""
+    X, y, group_shapes = movielens_like(6000, 150, 40, 3, seed=2)
+    y = np.clip(np.round(y), 1, 5) - 1
+    trainer, chain = make_pair(engine, oracle, X, y, 4, dtype, task="ordered", group_shapes=group_shapes)
+    assert_ordered_close(trainer, chain, dtype, "after init")
+    for it in range(6 if dtype == "f64" else 2):
+        trainer.step(1)
+        chain.step()
+        assert_ordered_close(trainer, chain, dtype, f"after sweep {it}")
+
+
+def test_ordered_probit_public_api(engine):
+    """The reference's own test (tests/oprobit/test_oprobit_1dim.py:9-61) through MyFMOrderedProbit:
+    planted cut-points recovered, predict_proba == manual Phi-differencing over the kept samples
+    == running mean of the per-iteration callback."""
+    from myfm_b200 import MyFMOrderedProbit
+    from myfm_b200.base import std_cdf
+    from myfm_b200.utils.callbacks import OrderedProbitCallback
+
+    X, y = ordinal_1dim()
+    with engine.engine_options(dtype="f64"):
+        callback = OrderedProbitCallback(100, X_test=X, y_test=y, n_class=4)
+        fm = MyFMOrderedProbit(0, fit_w0=False)
+        fm.fit(X, y, callback=callback, n_iter=100, n_kept_samples=100)
+        for cp_1, cp_2, cp_3 in fm.cutpoint_samples[-10:]:
+            assert abs(cp_1) < 0.25 and abs(cp_2 - cp_1 - 0.5) < 0.25 and abs(cp_3 - cp_1 - 1.5) < 0.25
+        p_core = fm.predict_proba(X)
+        np.testing.assert_allclose(callback.predictions / 100, p_core, rtol=1e-7, atol=1e-12)
+        manual = np.zeros((X.shape[0], 4))
+        for sample in fm.predictor_.samples:
+            score = sample.predict_score(X, [])
+            cdf = std_cdf(sample.cutpoints[0][np.newaxis, :] - score[:, np.newaxis])
+            diff = np.hstack([np.zeros((score.shape[0], 1)), cdf, np.ones((score.shape[0], 1))])
+            manual += diff[:, 1:] - diff[:, :-1]
+        manual /= len(fm.predictor_.samples)
+        np.testing.assert_allclose(manual, p_core, rtol=1e-7, atol=1e-12)
+        assert 0 < sum(fm.history_.n_mh_accept) <= 100 if hasattr(fm, "history_") else True
