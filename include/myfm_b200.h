@@ -98,6 +98,11 @@ typedef struct myfm_engine_options {
   int64_t row_offset; /* global index of this shard's first training row */
   int64_t n_rows_global;
   const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks, or NULL */
+  /* Dependency level of every main-table column, agreed between the ranks (the conflict graph of
+   * the GLOBAL matrix decides, a shard sees only part of it; myfm_b200/distributed.py runs the
+   * consensus with myfm_level_schedule / myfm_level_relax).  NULL = compute from this shard. */
+  const int32_t *column_level;
+  int64_t n_column_level;
 } myfm_engine_options_t;
 
 typedef struct myfm_trainer myfm_trainer_t;
@@ -203,6 +208,14 @@ int myfm_rng_fill(int32_t dtype, int32_t seed, int64_t n_skip_normals_persistent
  * every column; columns of one level are pairwise row-disjoint and running levels in order
  * reproduces the reference's serial column order exactly.  Returns the number of levels. */
 int myfm_level_schedule(const myfm_csr_t *X, int32_t *level, int32_t *n_levels);
+/* Same recurrence with `level` as lower bounds on entry: level[j] = max(level[j], 1 + max level of
+ * an earlier column sharing a row with j in X).  Row-sharded ranks alternate this with an
+ * element-wise MAX all-reduce until nothing changes; the fixed point is the schedule of the
+ * global matrix.  *changed = 1 when any entry grew. */
+int myfm_level_relax(const myfm_csr_t *X, int32_t *level, int32_t *n_levels, int32_t *changed);
+/* ncclGetUniqueId for the row-sharded trainer: rank 0 calls it and ships the 128 bytes to the
+ * other ranks by any side channel (myfm_b200/distributed.py uses torch.distributed). */
+int myfm_nccl_unique_id(void *out128);
 
 #ifdef __cplusplus
 }

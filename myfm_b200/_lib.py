@@ -77,6 +77,8 @@ class EngineOptions(C.Structure):
         ("row_offset", C.c_int64),
         ("n_rows_global", C.c_int64),
         ("nccl_unique_id", C.c_void_p),
+        ("column_level", C.POINTER(C.c_int32)),
+        ("n_column_level", C.c_int64),
     ]
 
 
@@ -90,7 +92,7 @@ EXPORTS = [
     "myfm_trainer_launch_count", "myfm_trainer_kernel_ms", "myfm_trainer_set_profiling",
     "myfm_dataset_create", "myfm_dataset_destroy", "myfm_predict_score", "myfm_predict_mean",
     "myfm_predict_oprobit_mean", "myfm_trainer_predict_score", "myfm_rng_fill",
-    "myfm_level_schedule",
+    "myfm_level_schedule", "myfm_level_relax", "myfm_nccl_unique_id",
 ]
 
 _lib: Optional[C.CDLL] = None

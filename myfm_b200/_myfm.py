@@ -539,6 +539,10 @@ class _TrainerHandle:
         eo.row_offset, eo.n_rows_global = opts.row_offset, opts.n_rows_global or X.shape[0]
         uid = (C.c_char * 128).from_buffer_copy(opts.nccl_unique_id) if opts.nccl_unique_id else None
         eo.nccl_unique_id = C.cast(uid, C.c_void_p) if uid is not None else None
+        levels = None
+        if opts.column_level is not None:
+            levels = np.ascontiguousarray(opts.column_level, dtype=np.int32)
+            eo.column_level, eo.n_column_level = _lib.ptr(levels, C.c_int32), levels.shape[0]
         cfg_struct = config._as_struct()
         h = C.c_void_p()
         _lib.check(_lib.lib().myfm_trainer_create(

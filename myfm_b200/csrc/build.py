@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmyfm_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "host_data.hpp", "rng.hpp", "../../include/myfm_b200.h"]
+HEADERS = ["common.cuh", "kernels.cuh", "host_data.hpp", "rng.hpp", "mt_device.cuh", "oprobit.cuh",
+           "../../include/myfm_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -21,6 +22,7 @@ NVCC_FLAGS = [
     # element-wise results must match the CPU path bit for bit: no FMA contraction
     "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+    "-ldl",  # NCCL is bound with dlopen at run time (row-sharded training only)
 ]
 
 

@@ -10,6 +10,9 @@
 #include "oprobit.cuh"
 #include "rng.hpp"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +24,50 @@ namespace {
 thread_local std::string g_last_error;
 
 constexpr int REDUCE_BLOCKS = 592; // 4 x 148 SMs
+
+// NCCL is bound at run time (dlopen by SONAME): a process that already carries an NCCL — the
+// one bundled with torch, when the host program uses torch.distributed next to this library —
+// must not end up with a second copy, and single-GPU use needs none at all.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+
+  static NcclApi &get() {
+    static NcclApi api = load();
+    return api;
+  }
+  static NcclApi load() {
+    NcclApi a;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle)
+        break;
+    }
+    if (!a.handle)
+      throw std::runtime_error("row-sharded training needs NCCL, but libnccl.so.2 could not be loaded.");
+    auto sym = [&](const char *n) {
+      void *p = dlsym(a.handle, n);
+      if (!p)
+        throw std::runtime_error(std::string("NCCL symbol missing: ") + n);
+      return p;
+    };
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    return a;
+  }
+  void check(ncclResult_t r, const char *what) const {
+    if (r != ncclSuccess)
+      throw CudaError(std::string("NCCL error in ") + what + ": " + GetErrorString(r));
+  }
+};
 
 int pow2_ceil_clamped(double x, int lo, int hi) {
   int v = lo;
@@ -293,7 +340,13 @@ template <typename Real> struct Trainer : TrainerBase {
   std::vector<DevRelationTrain<Real>> rel_train;
 
   int64_t N = 0, D = 0, D_all = 0;
+  int64_t N_global = 0; // training rows over all ranks (== N on one GPU)
   int K = -1, G = 0;
+  // row-sharded data parallelism: one rank per GPU, statistics summed with NCCL
+  int world = 1;
+  ncclComm_t comm = nullptr;
+  DevBuf<int> item_slot;
+  DevBuf<Real> colstat, told;
   std::vector<Real> y_host;
   DevBuf<Real> y;
   DevBuf<Real> eq_buf;         // interleaved {e_i, q_i}, [2 N]
@@ -340,8 +393,16 @@ template <typename Real> struct Trainer : TrainerBase {
     dtype = o.dtype;
     if (o.rng != MYFM_RNG_MT19937)
       throw std::runtime_error("rng=philox is not available in this build; use rng=mt19937.");
-    if (o.world_size > 1)
-      throw std::runtime_error("row-sharded multi-GPU training is not available in this build.");
+    world = o.world_size > 1 ? o.world_size : 1;
+    if (world > 1) {
+      if (!o.nccl_unique_id)
+        throw std::invalid_argument("world_size > 1 needs the ncclUniqueId shared by all ranks.");
+      if (n_rel > 0)
+        throw std::runtime_error("relation blocks are not supported with row-sharded training yet.");
+      if (cfg.task_type != MYFM_TASK_REGRESSION)
+        throw std::runtime_error("row-sharded training supports regression only: the reference's latent draws "
+                                 "for classification / ordered probit consume the mt19937 stream row by row.");
+    }
     HostCs<Real> Xh = host_from_api<Real>(X_api, "X");
     if (Xh.n_major != n_y) { // BaseFMTrainer.hpp:69-76
       std::ostringstream ss;
@@ -368,7 +429,24 @@ template <typename Real> struct Trainer : TrainerBase {
     {
       HostCs<Real> Xth0 = host_transpose(Xh);
       int n_levels = 0, primary = -1;
-      std::vector<int> level = compute_levels(Xth0, &n_levels);
+      std::vector<int> level;
+      if (o.column_level) { // agreed between the ranks (myfm_level_relax + max all-reduce)
+        if (o.n_column_level != Xth0.n_major)
+          throw std::invalid_argument("column_level must have one entry per main-table column.");
+        level.assign(o.column_level, o.column_level + o.n_column_level);
+        for (int lv : level) {
+          if (lv < 0)
+            throw std::invalid_argument("column_level must be non-negative.");
+          n_levels = std::max(n_levels, lv + 1);
+        }
+        int check_levels = 0;
+        if (compute_levels(Xth0, &check_levels, level.data()) != level)
+          throw std::invalid_argument("column_level is not a valid schedule for this shard.");
+      } else {
+        if (world > 1)
+          throw std::invalid_argument("row-sharded training needs column_level agreed between the ranks.");
+        level = compute_levels(Xth0, &n_levels);
+      }
       perm = primary_row_order(Xth0, level, n_levels, &primary);
       Xh = permute_rows(Xh, perm);
       main_unit = std::all_of(Xh.val.begin(), Xh.val.end(), [](Real v) { return v == Real(1); });
@@ -385,6 +463,11 @@ template <typename Real> struct Trainer : TrainerBase {
     perm_dev.upload(perm, stream);
     items.upload(plan.items, stream);
     seg_count.upload(plan.seg_count, stream);
+    if (world > 1) {
+      item_slot.upload(plan.item_slot, stream);
+      colstat.alloc(2 * static_cast<size_t>(std::max(1, plan.max_level_cols)));
+      told.alloc(std::max(1, plan.max_level_cols));
+    }
     seg_partial.alloc(2 * static_cast<size_t>(std::max(1, plan.max_seg_items)));
     seg_theta_old.alloc(std::max(1, plan.max_seg_items));
 
@@ -472,8 +555,17 @@ template <typename Real> struct Trainer : TrainerBase {
     scal.alloc(4);
     MYFM_CUDA(cudaStreamSynchronize(stream));
 
+    N_global = world > 1 ? o.n_rows_global : N;
+    if (world > 1) {
+      if (N_global < N)
+        throw std::invalid_argument("n_rows_global is smaller than this shard.");
+      NcclApi &nccl = NcclApi::get();
+      ncclUniqueId id;
+      std::memcpy(&id, o.nccl_unique_id, sizeof(id));
+      nccl.check(nccl.CommInitRank(&comm, world, id, o.rank), "ncclCommInitRank");
+    }
     // Gamma shapes are data independent (FMTrainer.hpp:140,157)
-    shape_alpha = (static_cast<Real>(cfg.alpha_0) + N) / 2;
+    shape_alpha = (static_cast<Real>(cfg.alpha_0) + N_global) / 2;
     shapes_lw.resize(G);
     for (int g = 0; g < G; g++) {
       Real a = static_cast<Real>(cfg.alpha_0) + static_cast<size_t>(cfg.feat_ptr[g + 1] - cfg.feat_ptr[g]);
@@ -486,6 +578,8 @@ template <typename Real> struct Trainer : TrainerBase {
       cudaStreamSynchronize(stream);
     if (rng_stream)
       cudaStreamSynchronize(rng_stream);
+    if (comm)
+      NcclApi::get().CommDestroy(comm);
     for (auto *evs : {z_copied, z_ready, z_free})
       for (int k = 0; k < 2; k++)
         if (evs[k])
@@ -663,6 +757,12 @@ template <typename Real> struct Trainer : TrainerBase {
     }
   };
 
+  void allreduce_sum(Real *buf, size_t n) {
+    NcclApi &nccl = NcclApi::get();
+    nccl.check(nccl.AllReduce(buf, buf, n, sizeof(Real) == 4 ? ncclFloat : ncclDouble, ncclSum, comm, stream),
+               "ncclAllReduce");
+  }
+
   // One level-ordered sweep over the main-table columns (w or one factor of V).
   template <bool IS_V>
   void sweep_main(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda,
@@ -681,6 +781,31 @@ template <typename Real> struct Trainer : TrainerBase {
       if (!grid)
         continue;
       TimedSpan span(timer, stream, 0);
+      if (world > 1) { // statistics -> sum over ranks -> identical draw everywhere -> local update
+        a.item_slot = item_slot.p + L.s0, a.colstat = colstat.p, a.told = told.p;
+        const int n_cols = L.end - L.s0 - (a.nS ? count_chunk_surplus(L) : 0);
+#define MYFM_DIST(U, C, UPD) k_level_dist<Real, IS_V, U, C, UPD><<<grid, SWEEP_THREADS, 0, stream>>>(a)
+#define MYFM_DIST_PHASE(UPD)                                                                       \
+  if (L.unit && L.contig)                                                                          \
+    MYFM_DIST(true, true, UPD);                                                                    \
+  else if (L.unit)                                                                                 \
+    MYFM_DIST(true, false, UPD);                                                                   \
+  else if (L.contig)                                                                               \
+    MYFM_DIST(false, true, UPD);                                                                   \
+  else                                                                                             \
+    MYFM_DIST(false, false, UPD);
+        MYFM_DIST_PHASE(false)
+        if (a.nS) {
+          k_level_chunk_fold<Real><<<ceil_div(a.nS, 128), 128, 0, stream>>>(a);
+          launched();
+        }
+        allreduce_sum(colstat.p, 2 * static_cast<size_t>(n_cols));
+        MYFM_DIST_PHASE(true)
+#undef MYFM_DIST_PHASE
+#undef MYFM_DIST
+        launched(2);
+        continue;
+      }
 #define MYFM_LEVEL(U, C)                                                                           \
   {                                                                                                \
     k_level_sweep<Real, IS_V, U, C><<<grid, SWEEP_THREADS, 0, stream>>>(a);                        \
@@ -703,6 +828,15 @@ template <typename Real> struct Trainer : TrainerBase {
   // q_init of the main table when it is one-hot shaped (all values 1, rows of equal length)
   bool main_unit = false;
   int main_row_len = 0;
+  // columns of a level = items minus the extra chunks of its long columns
+  int count_chunk_surplus(const SweepLevel &L) const {
+    int surplus = 0;
+    for (int i = L.s0; i < L.c0; i++)
+      if (plan.items[i].first == i - L.s0)
+        surplus += plan.seg_count[i] - 1;
+    return surplus;
+  }
+
   void spmv(const DevCs<Real> &A, const Real *x, Real *out, bool squared, int out_stride = 1) {
     if (!A.n_major)
       return;
@@ -961,6 +1095,16 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
 
+  // Row-sharded: the block partials of a grid reduction become one scalar summed over the ranks.
+  int fold_over_ranks() {
+    if (world == 1)
+      return REDUCE_BLOCKS;
+    k_fold_partials<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p);
+    launched();
+    allreduce_sum(partial.p, 1);
+    return 1;
+  }
+
   // update_all (BaseFMTrainer.hpp:135-152)
   void sweep() {
     const int slot = static_cast<int>(sweep_index & 1);
@@ -985,13 +1129,15 @@ template <typename Real> struct Trainer : TrainerBase {
 
     if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
       k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
-      k_finish_alpha<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p,
+      const int n_partial = fold_over_ranks();
+      k_finish_alpha<Real><<<1, 256, 0, stream>>>(n_partial, partial.p,
                                                    static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha);
       launched(2);
     }
     if (cfg.fit_w0) { // update_w0
       k_reduce_e<Real, 1><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
-      k_finish_w0<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p, static_cast<int>(N),
+      const int n_partial = fold_over_ranks();
+      k_finish_w0<Real><<<1, 256, 0, stream>>>(n_partial, partial.p, static_cast<int>(N_global),
                                                 static_cast<Real>(cfg.reg_0), h.alpha, z + L.z_w0, h.w0,
                                                 scal.p);
       k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, eq(), scal.p);
@@ -1562,6 +1708,35 @@ int myfm_rng_fill(int32_t dtype, int32_t seed, int64_t n_skip_normals_persistent
     run(float{});
   else
     run(double{});
+  MYFM_API_END
+}
+
+int myfm_nccl_unique_id(void *out128) {
+  MYFM_API_BEGIN
+  require(out128, "out128");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NcclApi &nccl = NcclApi::get();
+  ncclUniqueId id;
+  nccl.check(nccl.GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out128, &id, sizeof(id));
+  MYFM_API_END
+}
+
+int myfm_level_relax(const myfm_csr_t *X, int32_t *level, int32_t *n_levels, int32_t *changed) {
+  MYFM_API_BEGIN
+  require(X, "X"), require(n_levels, "n_levels"), require(changed, "changed");
+  HostCs<float> Xt = host_transpose(host_from_api<float>(*X, "X"));
+  if (Xt.n_major > 0)
+    require(level, "level");
+  int nl = 0;
+  std::vector<int> lv = compute_levels(Xt, &nl, level);
+  *changed = 0;
+  for (size_t j = 0; j < lv.size(); j++) {
+    if (lv[j] != level[j])
+      *changed = 1;
+    level[j] = lv[j];
+  }
+  *n_levels = nl;
   MYFM_API_END
 }
 

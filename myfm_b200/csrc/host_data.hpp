@@ -94,13 +94,15 @@ template <typename Real> bool has_duplicate_entries(const HostCs<Real> &csr) {
 // shares a row with it.  level(j) = 1 + max level of such earlier columns; columns of one level are
 // pairwise row-disjoint, so updating them concurrently and running the levels in order is the
 // serial sweep exactly.  One pass over the non-zeros.
+// `lower` (optional): lower bounds per column (level consensus between row shards).
 template <typename Real>
-std::vector<int> compute_levels(const HostCs<Real> &csc, int *n_levels_out) {
+std::vector<int> compute_levels(const HostCs<Real> &csc, int *n_levels_out,
+                                const int *lower = nullptr) {
   std::vector<int> next_level(csc.n_minor, 0); // per row: first level still free
   std::vector<int> level(csc.n_major, 0);
   int n_levels = csc.n_major ? 1 : 0;
   for (int64_t j = 0; j < csc.n_major; j++) {
-    int lv = 0;
+    int lv = lower ? lower[j] : 0;
     for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++)
       lv = std::max(lv, next_level[csc.idx[p]]);
     for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++)
@@ -207,6 +209,8 @@ struct SweepPlan {
   std::vector<SweepLevel> levels;
   std::vector<SweepItem> items;
   std::vector<int> seg_count; // S items: number of chunks of the column
+  std::vector<int> item_slot; // rank of the item's column among the level's columns (by index)
+  int max_level_cols = 0;
   int max_seg_items = 0;
   int primary_level = -1;
 };
@@ -280,9 +284,14 @@ SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level
       }
     }
     L.s0 = static_cast<int>(plan.items.size());
+    std::vector<int> by_index(c);
+    std::sort(by_index.begin(), by_index.end());
+    plan.max_level_cols = std::max(plan.max_level_cols, static_cast<int>(c.size()));
     auto push = [&](int j, int lo, int hi, int first, int count) {
       plan.items.push_back(SweepItem{j, lo, hi, first});
       plan.seg_count.push_back(count);
+      plan.item_slot.push_back(
+          static_cast<int>(std::lower_bound(by_index.begin(), by_index.end(), j) - by_index.begin()));
     };
     size_t k = 0;
     for (; k < c.size() && len(c[k]) > chunk; k++) {

@@ -398,6 +398,10 @@ template <typename Real> struct SweepArgs {
   const Real *mu;       // [G]
   Real *partial;        // [2 * nS] chunk statistics
   Real *theta_old_buf;  // [nS] value before the update, written by a column's first chunk
+  // row-sharded training (k_level_dist): statistics of every column of the level, summed over ranks
+  const int *item_slot; // column slot of every item (same numbering on every rank)
+  Real *colstat;        // [2 * columns of the level]
+  Real *told;           // [columns of the level] value before the update
 };
 
 template <typename Real, bool IS_V>
@@ -574,6 +578,94 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_level_seg_update(SweepArgs<Re
   if (b == first && threadIdx.x == 0)
     store_theta(a, j, theta_new);
   en.update(a, theta_old, theta_new);
+}
+
+// Row-sharded training: the rows of a column live on several GPUs, so every column takes the
+// two-phase route — local statistics (UPDATE = false), all-reduce of colstat over the ranks,
+// identical draw on every rank and local rank-1 update (UPDATE = true).
+template <typename Real, bool IS_V, bool UNIT, bool CONTIG, bool UPDATE>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_level_dist(SweepArgs<Real> a) {
+  __shared__ Real scratch[32];
+  const int b = blockIdx.x;
+  const bool cta_item = b < a.nS + a.nC;
+  const int lane = threadIdx.x & 31;
+  const int w = (b - a.nS - a.nC) * SWEEP_WARPS + (threadIdx.x >> 5);
+  if (!cta_item && w >= a.nW)
+    return;
+  const int item = cta_item ? b : a.nS + a.nC + w;
+  const int4 it = __ldg(a.item + item);
+  const int j = it.x, slot = a.item_slot[item];
+  const Real alpha = *a.alpha;
+  const bool leader = cta_item ? (threadIdx.x == 0 && (b >= a.nS || it.w == b)) : lane == 0;
+  if (!UPDATE) {
+    const Real theta_old = a.theta[j];
+    Real sq = 0, lin = 0;
+    if (cta_item) {
+      ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
+      en.load(a, it.y, it.z, threadIdx.x);
+      en.stats(theta_old, alpha, sq, lin);
+      sq = block_sum(sq, scratch);
+      lin = block_sum(lin, scratch);
+    } else {
+      ColumnEntries<Real, IS_V, UNIT, CONTIG, 32> en;
+      en.load(a, it.y, it.z, lane);
+      en.stats(theta_old, alpha, sq, lin);
+      sq = warp_sum(sq);
+      lin = warp_sum(lin);
+    }
+    if (b < a.nS && threadIdx.x == 0) // chunk of a long column: folded by k_level_chunk_fold
+      a.partial[2 * b] = sq, a.partial[2 * b + 1] = lin;
+    if (leader) {
+      a.told[slot] = theta_old;
+      if (b >= a.nS || !cta_item)
+        a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+    }
+  } else {
+    const int g = a.group[j];
+    const Real theta_old = a.told[slot];
+    const Real theta_new = column_draw<Real, IS_V>(a.colstat[2 * slot], a.colstat[2 * slot + 1], theta_old,
+                                                   alpha, a.lambda[g], a.mu[g], a.z[j]);
+    if (cta_item) {
+      ColumnEntries<Real, IS_V, UNIT, CONTIG, SWEEP_THREADS> en;
+      en.load(a, it.y, it.z, threadIdx.x);
+      en.update(a, theta_old, theta_new);
+    } else {
+      ColumnEntries<Real, IS_V, UNIT, CONTIG, 32> en;
+      en.load(a, it.y, it.z, lane);
+      en.update(a, theta_old, theta_new);
+    }
+    if (leader)
+      store_theta(a, j, theta_new);
+  }
+}
+
+// colstat[slot] of a long column = sum of its chunk statistics, in chunk order.
+template <typename Real> __global__ void k_level_chunk_fold(SweepArgs<Real> a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.nS)
+    return;
+  const int4 it = __ldg(a.item + b);
+  if (it.w != b)
+    return;
+  Real sq = 0, lin = 0;
+  for (int i = b; i < b + a.seg_count[b]; i++) {
+    sq += a.partial[2 * i];
+    lin += a.partial[2 * i + 1];
+  }
+  const int slot = a.item_slot[b];
+  a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+}
+
+// partial[0] = sum of n partial sums (one block), so that one scalar crosses the ranks
+template <typename Real> __global__ void k_fold_partials(int n, Real *partial) {
+  __shared__ Real scratch[32];
+  Real acc = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    acc += partial[i];
+  acc = block_sum(acc, scratch);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    partial[0] = acc;
 }
 
 // ----------------------------------------------------------------------------------------------

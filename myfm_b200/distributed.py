@@ -1,0 +1,132 @@
+"""Row-sharded data parallelism: one process per GPU (``torchrun``), every rank holds a contiguous
+range of the training rows and a replica of the model; the engine sums the per-column sufficient
+statistics of every dependency level with one NCCL all-reduce.
+
+``torch.distributed`` is plumbing only (rendezvous, two small host-side collectives at setup); it
+works with the ``gloo`` backend too, which is how the CPU test-suite covers this module.
+
+    import torch.distributed as dist, myfm_b200
+    from myfm_b200 import distributed as mdist
+    dist.init_process_group("nccl")
+    X_local, y_local, ctx = mdist.shard(X, y)            # or bring your own shard + mdist.context()
+    with ctx.options(dtype="f32"):
+        fm = myfm_b200.MyFMRegressor(rank=32).fit(X_local, y_local, group_shapes=...)
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+from scipy import sparse as sps
+
+from . import _lib
+from .options import engine_options
+
+
+def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of `rank`: the first n_rows % world_size ranks get one extra row."""
+    base, extra = divmod(int(n_rows), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def local_levels(X) -> np.ndarray:
+    """Dependency level of every column of this shard (myfm_level_schedule)."""
+    csr = _lib.CsrHolder(X)
+    level = np.zeros(max(1, csr.shape[1]), dtype=np.int32)
+    n_levels = C.c_int32()
+    _lib.check(_lib.lib().myfm_level_schedule(C.byref(csr.struct), _lib.ptr(level, C.c_int32), C.byref(n_levels)))
+    return level[:csr.shape[1]]
+
+
+def relax_levels(X, level: np.ndarray) -> Tuple[np.ndarray, bool]:
+    """One local relaxation with `level` as lower bounds (myfm_level_relax)."""
+    csr = _lib.CsrHolder(X)
+    out = np.ascontiguousarray(level, dtype=np.int32).copy()
+    if out.shape[0] == 0:
+        return out, False
+    n_levels, changed = C.c_int32(), C.c_int32()
+    _lib.check(_lib.lib().myfm_level_relax(C.byref(csr.struct), _lib.ptr(out, C.c_int32), C.byref(n_levels),
+                                           C.byref(changed)))
+    return out, bool(changed.value)
+
+
+def agree_on_levels(X_local, group=None, max_rounds: int = 1000) -> np.ndarray:
+    """The dependency-level schedule of the GLOBAL matrix, computed from row shards.
+
+    level(j) = 1 + max level of an earlier column sharing a row with j; a shard only sees the
+    conflicts of its own rows.  Every rank relaxes locally, the ranks take the element-wise
+    maximum, and the two steps repeat until no rank changes anything: the result is the least
+    fixed point, i.e. exactly what one process computes on the whole matrix.  One-hot fields
+    converge in the first round."""
+    import torch
+    import torch.distributed as dist
+
+    level = local_levels(X_local)
+    for _ in range(max_rounds):
+        t = torch.from_numpy(level.astype(np.int32))
+        dev = _collective_device(group)
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        level, changed = relax_levels(X_local, t.cpu().numpy())
+        flag = torch.tensor([int(changed)], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            return level
+    raise RuntimeError("dependency-level consensus did not converge")
+
+
+def _collective_device(group=None):
+    import torch
+    import torch.distributed as dist
+
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+@dataclass
+class ShardContext:
+    world_size: int
+    rank: int
+    row_offset: int
+    n_rows_global: int
+    nccl_unique_id: Optional[bytes]
+    column_level: np.ndarray
+
+    @contextlib.contextmanager
+    def options(self, **kwargs) -> Iterator[None]:
+        """engine_options(...) carrying this shard's description."""
+        with engine_options(world_size=self.world_size, rank=self.rank, row_offset=self.row_offset,
+                            n_rows_global=self.n_rows_global, nccl_unique_id=self.nccl_unique_id,
+                            column_level=self.column_level, **kwargs):
+            yield
+
+
+def context(X_local, row_offset: int, n_rows_global: int, group=None, with_nccl: bool = True) -> ShardContext:
+    """Collective: agrees on the level schedule and shares rank 0's ncclUniqueId."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    levels = agree_on_levels(X_local, group)
+    uid = None
+    if with_nccl and world > 1:
+        box = [None]
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check(_lib.lib().myfm_nccl_unique_id(C.cast(buf, C.c_void_p)))
+            box[0] = bytes(buf.raw)
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = box[0]
+    return ShardContext(world, rank, int(row_offset), int(n_rows_global), uid, levels)
+
+
+def shard(X, y, group=None, with_nccl: bool = True):
+    """Takes this rank's contiguous row range of a dataset every rank holds in full."""
+    import torch.distributed as dist
+
+    X = sps.csr_matrix(X)
+    lo, hi = shard_bounds(X.shape[0], dist.get_world_size(group), dist.get_rank(group))
+    X_local, y_local = X[lo:hi], np.asarray(y)[lo:hi]
+    return X_local, y_local, context(X_local, lo, X.shape[0], group, with_nccl)

@@ -28,6 +28,7 @@ class EngineOptions:
     row_offset: int = 0
     n_rows_global: int = 0
     nccl_unique_id: Optional[bytes] = None
+    column_level: Optional[object] = None  # int32 array: dependency level of every main-table column
 
 
 _current = EngineOptions()

@@ -1,0 +1,95 @@
+"""Row-sharded training on 2 GPUs (NCCL) against the single-GPU engine on the whole data.
+Needs two visible devices: run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import movielens_like
+
+    # heavy tail: the top movie is a multi-chunk column on each shard
+    return movielens_like(60001, 700, 25, 3, seed=11, zipf=(0.5, 1.2))
+
+
+def _config(group_shapes, n_iter):
+    from myfm_b200._myfm import ConfigBuilder
+
+    return (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(group_shapes)), group_shapes))
+            .set_n_iter(n_iter).set_n_kept_samples(n_iter).build())
+
+
+def _state(trainer):
+    w0, w, V, _ = trainer.get_fm()
+    h = trainer.get_hyper()
+    return np.concatenate([[w0], w, V.ravel(), [h.alpha], h.mu_w, h.lambda_w, h.mu_V.ravel(), h.lambda_V.ravel()])
+
+
+def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir: str) -> None:
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+
+    import myfm_b200
+    from myfm_b200 import distributed as mdist
+    from myfm_b200._myfm import _TrainerHandle
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        X, y, group_shapes = _data()
+        X_local, y_local, ctx = mdist.shard(X, y)
+        with ctx.options(dtype=dtype, device=rank):
+            t = _TrainerHandle(X_local, [], y_local, 42, _config(group_shapes, n_sweeps))
+            t.init_fm(6, 0.1)
+        states = []
+        for _ in range(n_sweeps):
+            t.step(1)
+            states.append(_state(t))
+        np.save(os.path.join(out_dir, f"states_{rank}.npy"), np.stack(states))
+        np.save(os.path.join(out_dir, f"e_{rank}.npy"), t.get_e())
+        del t
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_two_gpus_match_one(engine, dtype, tmp_path):
+    from myfm_b200 import _lib
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from myfm_b200._myfm import _TrainerHandle
+
+    n_sweeps = 4
+    mp.spawn(_worker, args=(2, _free_port(), dtype, n_sweeps, str(tmp_path)), nprocs=2, join=True)
+    X, y, group_shapes = _data()
+    with engine.engine_options(dtype=dtype):
+        t = _TrainerHandle(X, [], y, 42, _config(group_shapes, n_sweeps))
+        t.init_fm(6, 0.1)
+    got = [np.load(tmp_path / f"states_{r}.npy") for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])  # replicas stay bit-identical
+    tol = 1e-8 if dtype == "f64" else 2e-3
+    for it in range(n_sweeps):
+        t.step(1)
+        want = _state(t)
+        scale = np.maximum(np.abs(want), 1e-2)
+        assert np.max(np.abs(got[0][it] - want) / scale) < tol, f"sweep {it}"
+    e = np.concatenate([np.load(tmp_path / f"e_{r}.npy") for r in range(2)])
+    np.testing.assert_allclose(e, t.get_e(), rtol=tol, atol=tol)
