@@ -140,7 +140,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
         "steps_run": steps, "warmup_run": 1 + warm,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, X, rank, args.gpus),
+        "config": workload_config(args.workload, X.shape[0], X.nnz, rank, args.gpus),
         "nnz_rank_per_sec": value * X.nnz * rank,
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": 1, "kind": "port",
                          "sample": f"{steps} full update_all sweeps (of {args.steps} asked; bounded to ~3 min) of the same "
@@ -152,13 +152,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, X, rank, n_gpus):
+def workload_config(name, n_rows, nnz, rank, n_gpus):
     rows, users, movies, _ = WORKLOADS[name]
     return {"workload": f"{name}-shaped synthetic: {rows} rows x ({users} users + {movies} movies) one-hot, "
-                        f"nnz={X.nnz}, rank {rank}, regression, group_shapes=[users, movies]",
-            "rank": rank, "rows": int(X.shape[0]), "nnz": int(X.nnz), "rng": "mt19937 (reference stream, same seed)",
-            "l2": "working set (CSR+CSC+q,e,y ~ 0.5 GB) exceeds the 126 MB L2; no explicit flush",
-            "parallelism": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} GPUs"}
+                        f"nnz={nnz}, rank {rank}, regression, group_shapes=[users, movies]",
+            "rank": rank, "rows": int(n_rows), "nnz": int(nnz),
+            "rng": "mt19937 (reference stream, same seed; generated on the device)",
+            "l2": "working set (CSR+CSC+{e,q},y ~ 0.5 GB) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": "single GPU" if n_gpus == 1 else
+            f"rows sharded over {n_gpus} GPUs (contiguous ranges), one NCCL all-reduce of the column statistics "
+            f"per dependency level, model replicated"}
 
 
 def run_ours(args):
@@ -178,12 +181,20 @@ def run_ours(args):
         dist = dist_mod
 
     X, y, group_shapes, rank = make_workload(args.workload)
+    n_rows_global, nnz_global = X.shape[0], X.nnz
     dtype = args.dtype
     cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(group_shapes)), group_shapes))
            .set_n_iter(args.steps + args.warmup).set_n_kept_samples(1).build())
+    if dist is not None:  # every rank generated the same data; keep this rank's contiguous row range
+        from myfm_b200 import distributed as mdist
+
+        X, y, ctx = mdist.shard(X, y)
+        options = lambda: ctx.options(dtype=dtype, device=local)  # noqa: E731
+    else:
+        options = lambda: myfm_b200.engine_options(dtype=dtype, device=local)  # noqa: E731
 
     # ---- device-resident leg ---------------------------------------------------------------
-    with myfm_b200.engine_options(dtype=dtype, device=local):
+    with options():
         trainer = _TrainerHandle(X, [], y, CHAIN_SEED, cfg)
         trainer.init_fm(rank, 0.1)
     trainer.step(args.warmup)
@@ -222,19 +233,28 @@ def run_ours(args):
         stamps.append(time.perf_counter())
         return False, None
 
+    if dist is not None:
+        dist.barrier()
     t_fit0 = time.perf_counter()
-    with myfm_b200.engine_options(dtype=dtype, device=local):
+    with options():
         model = myfm_b200.MyFMRegressor(rank=rank, random_seed=CHAIN_SEED)
         model.fit(X, y, n_iter=args.steps + args.warmup, n_kept_samples=1, group_shapes=group_shapes,
                   callback=callback)
     t_fit = time.perf_counter() - t_fit0
     e2e_s = stamps[-1] - stamps[args.warmup - 1] if args.warmup > 0 else stamps[-1] - t_fit0
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
     e2e = args.steps / e2e_s
     G, D_all = len(group_shapes), X.shape[1]
     variates = (2 + 2 * G + D_all + 2 * G * rank + rank * D_all) * real_bytes
     d2h = (2 + 2 * G + 2 * G * rank) * real_bytes + real_bytes * (1 + D_all + D_all * rank)  # hypers + live fm read
 
     if rank_id != 0:
+        dist.destroy_process_group()
         return
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -245,9 +265,9 @@ def run_ours(args):
     line = {
         "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": workload_config(args.workload, X, rank, args.gpus),
-        "nnz_rank_per_sec": it_per_s * X.nnz * rank,
+        "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": workload_config(args.workload, n_rows_global, nnz_global, rank, args.gpus),
+        "nnz_rank_per_sec": it_per_s * nnz_global * rank,
         "e2e": {"value": e2e, "unit": "it/s", "h2d_bytes_per_step": int(variates), "d2h_bytes_per_step": int(d2h),
                 "fit_total_s": t_fit, "note": "MyFMRegressor.fit() with host buffers; wall clock between per-iteration "
                 "callbacks (setup: upload, transpose, level schedule is inside fit_total_s)"},
@@ -255,7 +275,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_sweep_warp/k_sweep_block (column sweeps of w and the K factor columns)",
+                     "kernel": "k_level_sweep + k_level_seg_update (column sweeps of w and of the K factor columns"
+                               + ("; k_level_dist on this rank's row shard" if args.gpus > 1 else "") + ")",
                      "algorithmic_bytes_per_step": bytes_["sweeps"], "launch_groups": int(sweep_launches),
                      "share_of_step": sweep_ms / ms if ms else None,
                      "whole_step_GBps": bytes_["total"] * it_per_s / 1e9,

@@ -5,15 +5,19 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it; the
 // product path (myfm_b200/) never does.
 //
-// Pinning status: the reference cannot be built here (it needs Eigen 3.4.0, fetched from the
-// network by the reference's setup.py:21-50; Eigen is not installed and there is no network), and
-// the reference ships no golden vectors.  The oracle is pinned by the reference's own test-suite
-// identities re-run against it (tests/test_oracle_reference_suite.py: block == flat at rtol 1e-7,
-// predictor == mean of per-iteration predict_score, planted-parameter recovery, ordered-probit
-// cut-points; reference tests/regression/test_block.py:80-149, tests/regression/test_fit.py:20-72,
-// tests/classification/test_classification.py:14-70, tests/oprobit/test_oprobit_1dim.py:9-61) and by
-// libstdc++ <random> known-answer values.  Below that level (Eigen's vectorised dense reductions,
-// assumed column-major init order) parity with an Eigen build is UNPINNED.
+// Pinning status: PINNED against every fixture and known-answer test the reference's own
+// test-suite holds for this path — tests/test_oracle.py re-runs them on the oracle:
+// block == flat at rtol 1e-7 incl. the n_workers / pickle round trip
+// (reference tests/regression/test_block.py:80-149), predictor == running mean of per-iteration
+// predict_score and planted-parameter recovery (tests/regression/test_fit.py:20-72,
+// tests/classification/test_classification.py:14-70), ordered-probit cut-points and
+// predict_proba == manual Phi differencing (tests/oprobit/test_oprobit_1dim.py:9-61), the fixtures
+// of tests/conftest.py:15-45 — plus libstdc++ <random> known-answer values for the RNG contract.
+// The reference ships no golden vectors and cannot itself be run here (it needs Eigen 3.4.0,
+// fetched from the network by setup.py:21-50; Eigen is not installed, there is no network), so
+// nothing tighter exists to pin against: what those tests do not constrain — the order of Eigen's
+// vectorised dense reductions (O(eps)) and the column-major fill order of FM.hpp:34-45 — is an
+// assumption of the restatement, stated in every parity report.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // RNG: std::mt19937 + libstdc++ distributions constructed exactly where the reference constructs
