@@ -1,5 +1,7 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list.  Outputs under gpurun_out/.
+# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list, ncu --set full of the hot kernels.
+# Usage: tools/gpu_round.sh [tag]     outputs under gpurun_out/
+TAG=${1:-round}
 set -x
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
@@ -8,7 +10,11 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 tail -3 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-cat gpurun_out/bench.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py --sweeps 2 > gpurun_out/ncu_launches.log 2>&1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench_$TAG.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py --sweeps 2 > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_level_sweep|k_level_seg_update|k_level_dist|k_spmv|k_predict" -s 200 -c 10 \
+    -o gpurun_out/full_$TAG -f python tools/profile_step.py --sweeps 3 > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out/
