@@ -89,7 +89,7 @@ EXPORTS = [
     "myfm_trainer_sync", "myfm_trainer_timed_steps", "myfm_trainer_dims", "myfm_trainer_get_fm", "myfm_trainer_get_cutpoints",
     "myfm_trainer_get_hyper", "myfm_trainer_get_e", "myfm_trainer_get_q", "myfm_trainer_set_state",
     "myfm_trainer_mh_accept", "myfm_trainer_get_variates",
-    "myfm_trainer_launch_count", "myfm_trainer_kernel_ms", "myfm_trainer_set_profiling",
+    "myfm_trainer_sweep_path", "myfm_trainer_launch_count", "myfm_trainer_kernel_ms", "myfm_trainer_set_profiling",
     "myfm_dataset_create", "myfm_dataset_destroy", "myfm_predict_score", "myfm_predict_mean",
     "myfm_predict_oprobit_mean", "myfm_trainer_predict_score", "myfm_rng_fill",
     "myfm_level_schedule", "myfm_level_relax", "myfm_nccl_unique_id",

@@ -649,6 +649,12 @@ class _TrainerHandle:
         _lib.check(_lib.lib().myfm_trainer_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def sweep_path(self) -> int:
+        """0 = general dependency-level kernels, 1 = field path (csrc/field_sweep.cuh)."""
+        n = C.c_int32()
+        _lib.check(_lib.lib().myfm_trainer_sweep_path(self._h, C.byref(n)))
+        return int(n.value)
+
     def set_profiling(self, on: bool) -> None:
         _lib.check(_lib.lib().myfm_trainer_set_profiling(self._h, C.c_int32(int(on))))
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "host_data.hpp"
 #include "kernels.cuh"
+#include "field_sweep.cuh"
 #include "mt_device.cuh"
 #include "oprobit.cuh"
 #include "rng.hpp"
@@ -304,6 +305,7 @@ struct TrainerBase {
                          const double *mu_w, const double *lambda_w, const double *mu_V,
                          const double *lambda_V, const double *e) = 0;
   virtual int64_t launch_count() const = 0;
+  virtual int sweep_path() const = 0;
   virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
   virtual void set_profiling(bool on) = 0;
   virtual void predict_score(DatasetBase *d, double *out) = 0;
@@ -338,6 +340,15 @@ template <typename Real> struct Trainer : TrainerBase {
   DevBuf<Real> seg_partial, seg_theta_old;
   DevBuf<Real> dense_tmp; // [N] staging for boundary copies of e / q
   std::vector<DevRelationTrain<Real>> rel_train;
+
+  // field path (field_sweep.cuh): main table = stack of position-aligned fields
+  bool field_path = false;
+  int f_tail = 0, f_last_base = 0, f_tab = 0, f_sm_count = 0, f_launch = 0;
+  bool f_pending_valid = false; // the last level's draw of the previous vector awaits the next pass
+  SweepLevel f_level0, f_levelL;
+  DevBuf<SweepItem> f_items0, f_itemsL;
+  DevBuf<int> f_seg_countL, f_tail_idx, f_sched;
+  DevBuf<Real> f_tail_val, f_own_val, f_pend_told, f_pend_tnew, f_partial;
 
   int64_t N = 0, D = 0, D_all = 0;
   int64_t N_global = 0; // training rows over all ranks (== N on one GPU)
@@ -458,6 +469,7 @@ template <typename Real> struct Trainer : TrainerBase {
       plan = make_sweep_plan(Xth, level, n_levels, SWEEP_WARP_MAX, SWEEP_CHUNK);
       plan.primary_level = primary;
       Xt.upload(Xth, stream);
+      setup_field_path(Xh, Xth, level, n_levels, n_rel);
       MYFM_CUDA(cudaStreamSynchronize(stream));
     }
     perm_dev.upload(perm, stream);
@@ -766,7 +778,7 @@ template <typename Real> struct Trainer : TrainerBase {
   // One level-ordered sweep over the main-table columns (w or one factor of V).
   template <bool IS_V>
   void sweep_main(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda,
-                  const Real *mu) {
+                  const Real *mu, size_t first_level = 0, size_t end_level = static_cast<size_t>(-1)) {
     SweepArgs<Real> a;
     a.idx = Xt.idx.p, a.val = Xt.val.p;
     a.eq = eq();
@@ -774,7 +786,8 @@ template <typename Real> struct Trainer : TrainerBase {
     a.z = z, a.group = group.p;
     a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
     a.partial = seg_partial.p, a.theta_old_buf = seg_theta_old.p;
-    for (const SweepLevel &L : plan.levels) {
+    for (size_t li = first_level; li < std::min(end_level, plan.levels.size()); li++) {
+      const SweepLevel &L = plan.levels[li];
       a.item = reinterpret_cast<const int4 *>(items.p + L.s0), a.seg_count = seg_count.p + L.s0;
       a.nS = L.c0 - L.s0, a.nC = L.w0 - L.c0, a.nW = L.end - L.w0;
       const int grid = a.nS + a.nC + ceil_div(a.nW, SWEEP_WARPS);
@@ -824,6 +837,155 @@ template <typename Real> struct Trainer : TrainerBase {
       launched(a.nS ? 2 : 1);
     }
   }
+
+  // ---- field path (field_sweep.cuh) ---------------------------------------------------------------
+  // Decides whether the main table is a stack of position-aligned fields and, if so, builds the
+  // extra arrays of that path.  Xh: CSR in device row order, Xth its transpose.
+  void setup_field_path(const HostCs<Real> &Xh, const HostCs<Real> &Xth, const std::vector<int> &level,
+                        int n_levels, int n_rel) {
+    field_path = false;
+    const char *off = std::getenv("MYFM_NO_FIELD_PATH");
+    if (off && off[0] == '1')
+      return;
+    const int L = main_row_len;
+    const int64_t n = Xh.n_major;
+    if (world > 1 || n_rel > 0 || n == 0 || L < 2 || L != n_levels || plan.primary_level != 0 ||
+        !plan.levels[0].contig)
+      return;
+    for (int64_t i = 0; i < n; i++)
+      for (int k = 0; k < L; k++)
+        if (level[Xh.idx[i * L + k]] != k)
+          return;
+    int lo = std::numeric_limits<int>::max(), hi = -1, longest0 = 0;
+    for (int64_t j = 0; j < Xth.n_major; j++) {
+      if (level[j] == L - 1)
+        lo = std::min<int>(lo, j), hi = std::max<int>(hi, j);
+      if (level[j] == 0)
+        longest0 = std::max(longest0, Xth.ptr[j + 1] - Xth.ptr[j]);
+    }
+    if (hi < 0 || longest0 > FIELD_CTA_MAX)
+      return;
+    int dev_smem = 0;
+    MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    MYFM_CUDA(cudaDeviceGetAttribute(&f_sm_count, cudaDevAttrMultiProcessorCount, device));
+    const int64_t tab = static_cast<int64_t>(hi) - lo + 1;
+    if (tab * 3 * static_cast<int64_t>(sizeof(Real)) > dev_smem - 2048)
+      return;
+    f_last_base = lo, f_tab = static_cast<int>(tab), f_tail = L - 1;
+
+    SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_WARP_MAX, FIELD_CTA_MAX, 0);
+    SweepPlan pL = make_sweep_plan(Xth, level, n_levels, STATS_WARP_MAX, STATS_CHUNK, L - 1);
+    f_level0 = p0.levels[0], f_levelL = pL.levels[L - 1];
+    // level-0 items carry row ranges: a contiguous column's rows are idx[lo] .. idx[lo] + len
+    for (SweepItem &it : p0.items) {
+      const int len = it.hi - it.lo;
+      const int first_row = len ? Xth.idx[it.lo] : 0;
+      it.lo = first_row, it.hi = first_row + len;
+    }
+    f_items0.upload(p0.items, stream);
+    f_itemsL.upload(pL.items, stream);
+    f_seg_countL.upload(pL.seg_count, stream);
+    f_partial.alloc(2 * static_cast<size_t>(std::max(1, f_levelL.c0 - f_levelL.s0)));
+    std::vector<int> tail(static_cast<size_t>(f_tail) * n);
+    for (int64_t i = 0; i < n; i++)
+      for (int k = 1; k < L; k++)
+        tail[static_cast<size_t>(k - 1) * n + i] = Xh.idx[i * L + k];
+    f_tail_idx.upload(tail, stream);
+    if (!main_unit) {
+      std::vector<Real> tv(static_cast<size_t>(f_tail) * n), ov(n);
+      for (int64_t i = 0; i < n; i++) {
+        ov[i] = Xh.val[i * L];
+        for (int k = 1; k < L; k++)
+          tv[static_cast<size_t>(k - 1) * n + i] = Xh.val[i * L + k];
+      }
+      f_tail_val.upload(tv, stream);
+      f_own_val.upload(ov, stream);
+    }
+    f_pend_told.alloc(f_tab);
+    f_pend_tnew.alloc(f_tab);
+    f_pend_told.zero(stream);
+    f_pend_tnew.zero(stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream)); // host staging vectors die here
+    field_path = true;
+  }
+
+  template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a) {
+    auto kernel = k_field_stream<Real, IS_V, UNIT, PEND>;
+    const size_t smem = 3 * static_cast<size_t>(f_tab) * sizeof(Real);
+    static size_t configured = 0; // per instantiation
+    if (smem > configured) {
+      MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+      configured = smem;
+    }
+    kernel<<<f_sm_count, FIELD_THREADS, smem, stream>>>(a);
+    launched();
+  }
+
+  // One vector (w or a factor column) over the main table: streaming pass, middle levels, gather.
+  template <bool IS_V>
+  void sweep_field(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda,
+                   const Real *mu) {
+    TimedSpan span(timer, stream, 0);
+    const int pend = !f_pending_valid ? PEND_NONE : (IS_V && f_pending_is_v ? PEND_V : PEND_W);
+    {
+      FieldStreamArgs<Real> a;
+      a.item = reinterpret_cast<const int4 *>(f_items0.p + f_level0.s0);
+      a.nC = f_level0.w0 - f_level0.s0, a.nW = f_level0.end - f_level0.w0;
+      a.sched = f_sched.p + (f_launch++);
+      a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
+      a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;
+      a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
+      a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
+      a.last_base = f_last_base, a.n_tab = f_tab;
+      a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
+#define MYFM_FS(V, P)                                                                              \
+  if (main_unit)                                                                                   \
+    launch_field_stream<V, true, P>(a);                                                            \
+  else                                                                                             \
+    launch_field_stream<V, false, P>(a);
+      if (!IS_V) {
+        if (pend != PEND_NONE)
+          throw std::logic_error("field path: the w sweep must not find a pending update.");
+        MYFM_FS(false, PEND_NONE)
+      } else if (pend == PEND_NONE) {
+        MYFM_FS(true, PEND_NONE)
+      } else if (pend == PEND_W) {
+        MYFM_FS(true, PEND_W)
+      } else {
+        MYFM_FS(true, PEND_V)
+      }
+#undef MYFM_FS
+    }
+    if (f_tail > 1)
+      sweep_main<IS_V>(theta, theta_t, t_stride, z, lambda, mu, 1, static_cast<size_t>(f_tail));
+    {
+      FieldStatsArgs<Real> a;
+      a.idx = Xt.idx.p, a.val = Xt.val.p;
+      a.item = reinterpret_cast<const int4 *>(f_itemsL.p + f_levelL.s0);
+      a.seg_count = f_seg_countL.p + f_levelL.s0;
+      a.nS = f_levelL.c0 - f_levelL.s0, a.nC = f_levelL.w0 - f_levelL.c0, a.nW = f_levelL.end - f_levelL.w0;
+      a.eq = eq();
+      a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
+      a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
+      a.partial = f_partial.p, a.last_base = f_last_base;
+      a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
+      const int grid = a.nS + a.nC + ceil_div(a.nW, STATS_THREADS / 32);
+      if (grid) {
+        if (main_unit)
+          k_field_stats<Real, IS_V, true><<<grid, STATS_THREADS, 0, stream>>>(a);
+        else
+          k_field_stats<Real, IS_V, false><<<grid, STATS_THREADS, 0, stream>>>(a);
+        launched();
+        if (a.nS) {
+          k_field_finish_long<Real, IS_V><<<ceil_div(a.nS, 128), 128, 0, stream>>>(a);
+          launched();
+        }
+      }
+    }
+    f_pending_valid = true, f_pending_is_v = IS_V;
+  }
+  bool f_pending_is_v = false;
 
   // q_init of the main table when it is one-hot shaped (all values 1, rows of equal length)
   bool main_unit = false;
@@ -896,7 +1058,10 @@ template <typename Real> struct Trainer : TrainerBase {
       w.zero(stream); // e keeps the stale contribution until update_e, as in the reference
       return;
     }
-    sweep_main<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
+    if (field_path)
+      sweep_field<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
+    else
+      sweep_main<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
     const int n = static_cast<int>(N);
     for (size_t b = 0; b < data.rels.size(); b++) {
       auto &d = data.rels[b];
@@ -924,6 +1089,10 @@ template <typename Real> struct Trainer : TrainerBase {
       Real *Vr = V.p + static_cast<size_t>(D_all) * r;
       const Real *z = z_all + static_cast<size_t>(D_all) * r;
       const Real *lam = h.lambda_V + static_cast<size_t>(G) * r, *mu = h.mu_V + static_cast<size_t>(G) * r;
+      if (field_path) {
+        sweep_field<true>(Vr, Vt.p + r, K, z, lam, mu);
+        continue;
+      }
       {
         TimedSpan span(timer, stream, 1);
         if (D)
@@ -1126,6 +1295,12 @@ template <typename Real> struct Trainer : TrainerBase {
     z_last = z;
     HyperView<Real> h = hv();
     const SweepLayout &L = layout;
+    if (field_path) { // work counters of this sweep's streaming passes; nothing is pending after update_e
+      if (f_sched.n < static_cast<size_t>(K) + 2)
+        f_sched.alloc(static_cast<size_t>(K) + 2);
+      f_sched.zero(stream);
+      f_launch = 0, f_pending_valid = false;
+    }
 
     if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
       k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
@@ -1160,6 +1335,7 @@ template <typename Real> struct Trainer : TrainerBase {
       launched();
     }
     update_V(z + L.z_V);
+    f_pending_valid = false; // update_e overwrites e: the last vector's pending update is dropped
     { // update_e
       TimedSpan span(timer, stream, 2);
       data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e_ptr(), 2);
@@ -1266,6 +1442,8 @@ template <typename Real> struct Trainer : TrainerBase {
       out[i] = h[i];
   }
   void get_q(double *out) override {
+    if (field_path && K > 0) // the field path leaves q undefined between sweeps: q = X V[:, K-1]
+      spmv(data.X, V.p + static_cast<size_t>(D_all) * (K - 1), q_ptr(), false, 2);
     std::vector<Real> h(N);
     export_component(1, h.data());
     for (int64_t i = 0; i < N; i++)
@@ -1327,6 +1505,7 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
   int64_t launch_count() const override { return launches; }
+  int sweep_path() const override { return field_path ? 1 : 0; }
   void kernel_ms(int family, double *ms, int64_t *n) override {
     sync();
     if (family < 0 || family > 2)
@@ -1590,6 +1769,12 @@ int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count) {
   MYFM_API_BEGIN
   require(t, "trainer"), require(count, "count");
   *count = t->impl->launch_count();
+  MYFM_API_END
+}
+int myfm_trainer_sweep_path(const myfm_trainer_t *t, int32_t *path) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(path, "path");
+  *path = t->impl->sweep_path();
   MYFM_API_END
 }
 int myfm_trainer_set_profiling(myfm_trainer_t *t, int32_t on) {

@@ -263,15 +263,20 @@ HostCs<Real> permute_rows(const HostCs<Real> &csr, const std::vector<int> &perm)
 
 template <typename Real>
 SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level, int n_levels,
-                          int warp_max, int chunk) {
+                          int warp_max, int chunk, int only_level = -1) {
   SweepPlan plan;
   plan.levels.resize(n_levels);
   std::vector<std::vector<int>> cols(n_levels);
   for (int64_t j = 0; j < csc.n_major; j++)
-    cols[level[j]].push_back(static_cast<int>(j));
+    if (only_level < 0 || level[j] == only_level)
+      cols[level[j]].push_back(static_cast<int>(j));
   auto len = [&](int j) { return csc.ptr[j + 1] - csc.ptr[j]; };
   for (int l = 0; l < n_levels; l++) {
     SweepLevel &L = plan.levels[l];
+    if (only_level >= 0 && l != only_level) {
+      L.s0 = L.c0 = L.w0 = L.end = static_cast<int>(plan.items.size());
+      continue;
+    }
     std::vector<int> &c = cols[l];
     std::stable_sort(c.begin(), c.end(), [&](int x, int y) { return len(x) > len(y); });
     for (int j : c) {

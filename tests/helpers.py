@@ -132,3 +132,29 @@ def dense_block_data(n_train: int = 400, seed: int = 3):
     y = (X_flatten.dot(w) + 0.5 * (((X_flatten.dot(F.T)) ** 2).sum(1) - X2.dot((F ** 2).sum(0)))
          + 0.5 * rns.randn(n_train))
     return X_flatten, main, (user_indices, user_block), (item_indices, item_block), y, group_shapes
+
+
+def fields_like(n_rows: int, field_sizes, rank: int, seed: int, unit: bool = True, zipf: float = 0.8,
+                noise: float = 0.5):
+    """L categorical fields per row (one active category each, sorted column order), power-law
+    popularity; values 1 (`unit`) or random in [0.5, 1.5].  Planted rank-`rank` FM + noise."""
+    rng = np.random.default_rng(seed)
+    L = len(field_sizes)
+    offsets = np.concatenate([[0], np.cumsum(field_sizes)])
+    cols = np.empty((n_rows, L), dtype=np.int32)
+    for f, n in enumerate(field_sizes):
+        p = 1.0 / np.arange(1, n + 1) ** zipf
+        c = rng.choice(n, size=n_rows, p=p / p.sum())
+        if n_rows >= n:
+            where = rng.permutation(n_rows)[:n]
+            c[where] = rng.permutation(n)  # every category appears
+        cols[:, f] = offsets[f] + c
+    vals = np.ones((n_rows, L)) if unit else rng.uniform(0.5, 1.5, size=(n_rows, L))
+    indptr = np.arange(0, L * n_rows + 1, L, dtype=np.int64)
+    X = sps.csr_matrix((vals.ravel(), cols.ravel(), indptr), shape=(n_rows, int(offsets[-1])))
+    w = rng.normal(0, 0.3, X.shape[1])
+    F = rng.normal(0, 0.4, (rank, X.shape[1]))
+    X2 = X.copy()
+    X2.data = X2.data ** 2
+    y = 1.0 + X.dot(w) + 0.5 * ((X.dot(F.T) ** 2).sum(1) - X2.dot((F ** 2).sum(0))) + rng.normal(0, noise, n_rows)
+    return X, y, list(field_sizes)

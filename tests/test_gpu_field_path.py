@@ -1,0 +1,107 @@
+"""The field path of the column sweeps (myfm_b200/csrc/field_sweep.cuh: streaming level 0 with the
+fused q_init and the deferred last-level update, gather-only last level) against the oracle and
+against the general dependency-level kernels, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import fields_like, movielens_like
+from test_gpu_parity import assert_state_close, make_pair, run_chain_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_path_selection(engine, oracle):
+    X, y, gs = movielens_like(5000, 60, 20, 3, seed=1)
+    t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
+    assert t.sweep_path() == 1
+    os.environ["MYFM_NO_FIELD_PATH"] = "1"
+    try:
+        t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
+        assert t.sweep_path() == 0
+    finally:
+        del os.environ["MYFM_NO_FIELD_PATH"]
+    # ragged rows (a row without its second field) are not a field stack
+    Xr = X.tolil()
+    Xr[0, X[0].indices[1]] = 0
+    Xr = Xr.tocsr()
+    Xr.eliminate_zeros()
+    t, _ = make_pair(engine, oracle, Xr, y, 3, "f64", group_shapes=gs)
+    assert t.sweep_path() == 0
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_long_columns(engine, oracle, dtype):
+    """Heavy-tailed fields: level-0 columns above 1024 rows (whole CTA), 256..1024 (warp, two
+    passes), below (registers); last-level columns above 8192 entries (chunked statistics)."""
+    X, y, gs = movielens_like(60000, 200, 12, 4, seed=3, zipf=1.0)
+    lens = np.diff(X.tocsc().indptr)
+    assert lens[:200].max() > 1024 and lens[200:].max() > 8192 and lens[:200].min() < 256
+    t, chain = make_pair(engine, oracle, X, y, 4, dtype, group_shapes=gs)
+    assert t.sweep_path() == 1
+    run_chain_parity(t, chain, dtype, 6 if dtype == "f64" else 3)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_three_fields_with_values(engine, oracle, dtype):
+    """Three fields, non-unit values: the middle level runs the general gather/scatter kernel
+    between the streaming pass and the gather-only level."""
+    X, y, gs = fields_like(8000, [50, 30, 20], 3, seed=5, unit=False)
+    t, chain = make_pair(engine, oracle, X, y, 5, dtype, group_shapes=gs)
+    assert t.sweep_path() == 1
+    run_chain_parity(t, chain, dtype, 6 if dtype == "f64" else 3)
+
+
+def test_four_unit_fields(engine, oracle):
+    X, y, gs = fields_like(6000, [40, 25, 10, 7], 3, seed=6, unit=True)
+    t, chain = make_pair(engine, oracle, X, y, 4, "f64", group_shapes=gs)
+    assert t.sweep_path() == 1
+    run_chain_parity(t, chain, "f64", 5)
+
+
+@pytest.mark.parametrize("kw", [dict(fit_linear=False), dict(fit_w0=False), dict(fit_linear=False, fit_w0=False)])
+def test_without_linear_or_bias(engine, oracle, kw):
+    """fit_linear=False: the first factor's streaming pass finds nothing pending."""
+    X, y, gs = movielens_like(8000, 80, 30, 3, seed=7)
+    t, chain = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs, **kw)
+    assert t.sweep_path() == 1
+    run_chain_parity(t, chain, "f64", 5)
+
+
+def test_rank_zero_and_one(engine, oracle):
+    X, y, gs = movielens_like(4000, 50, 20, 2, seed=8)
+    for rank in (0, 1):
+        t, chain = make_pair(engine, oracle, X, y, rank, "f64", group_shapes=gs)
+        run_chain_parity(t, chain, "f64", 4)
+
+
+@pytest.mark.parametrize("task", ["classification", "ordered"])
+def test_latent_tasks(engine, oracle, task):
+    X, y, gs = movielens_like(3000, 40, 15, 2, seed=9)
+    if task == "classification":
+        y = (y > np.median(y)).astype(np.float64) * 2 - 1
+    else:
+        y = np.digitize(y, np.quantile(y, [0.33, 0.66])).astype(np.float64)
+    t, chain = make_pair(engine, oracle, X, y, 3, "f64", task=task, group_shapes=gs)
+    assert t.sweep_path() == 1
+    run_chain_parity(t, chain, "f64", 4)
+
+
+def test_field_path_equals_general_path(engine, oracle):
+    """Same chain through both schedules: they differ in summation order only."""
+    X, y, gs = fields_like(20000, [300, 60], 4, seed=10, unit=False)
+    a, _ = make_pair(engine, oracle, X, y, 6, "f64", group_shapes=gs)
+    os.environ["MYFM_NO_FIELD_PATH"] = "1"
+    try:
+        b, _ = make_pair(engine, oracle, X, y, 6, "f64", group_shapes=gs)
+    finally:
+        del os.environ["MYFM_NO_FIELD_PATH"]
+    assert (a.sweep_path(), b.sweep_path()) == (1, 0)
+    for it in range(5):
+        a.step(1)
+        b.step(1)
+        for xa, xb in zip(a.get_fm()[:3], b.get_fm()[:3]):
+            np.testing.assert_allclose(xa, xb, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(a.get_e(), b.get_e(), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(a.get_q(), b.get_q(), rtol=1e-9, atol=1e-9)

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="ml10m")
 ap.add_argument("--sweeps", type=int, default=2)
 ap.add_argument("--dtype", default="f32")
+ap.add_argument("--families", action="store_true", help="per-family CUDA-event times")
 args = ap.parse_args()
 
 X, y, group_shapes, rank = bench.make_workload(args.workload)
@@ -28,5 +29,13 @@ cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(gro
 with myfm_b200.engine_options(dtype=args.dtype):
     t = _TrainerHandle(X, [], y, bench.CHAIN_SEED, cfg)
     t.init_fm(rank, 0.1)
+t.timed_steps(3)  # warm-up
+if args.families:
+    t.set_profiling(True)
 ms = t.timed_steps(args.sweeps)
+if args.families:
+    for fam, name in enumerate(("column_sweeps", "q_init", "e_refresh")):
+        fms, n = t.kernel_ms(fam)
+        print(f"  {name}: {fms / args.sweeps:.3f} ms/sweep in {n // args.sweeps} launch groups")
+print(f"sweep path = {t.sweep_path()}")
 print(f"{args.sweeps} sweeps: {ms / args.sweeps:.2f} ms/sweep, launches={t.launch_count()}")
