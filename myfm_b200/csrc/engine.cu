@@ -344,6 +344,7 @@ template <typename Real> struct Trainer : TrainerBase {
   // field path (field_sweep.cuh): main table = stack of position-aligned fields
   bool field_path = false;
   int f_tail = 0, f_last_base = 0, f_tab = 0, f_sm_count = 0, f_launch = 0;
+  int f_nCC = 0, f_nCR = 0, f_nG = 0, f_nW = 0; // level-0 columns by length class (k_field_stream)
   bool f_pending_valid = false; // the last level's draw of the previous vector awaits the next pass
   SweepLevel f_level0, f_levelL;
   DevBuf<SweepItem> f_items0, f_itemsL;
@@ -873,14 +874,24 @@ template <typename Real> struct Trainer : TrainerBase {
       return;
     f_last_base = lo, f_tab = static_cast<int>(tab), f_tail = L - 1;
 
-    SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_WARP_MAX, FIELD_CTA_MAX, 0);
+    SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_CTA_MAX, FIELD_CTA_MAX, 0); // longest first
     SweepPlan pL = make_sweep_plan(Xth, level, n_levels, STATS_WARP_MAX, STATS_CHUNK, L - 1);
     f_level0 = p0.levels[0], f_levelL = pL.levels[L - 1];
     // level-0 items carry row ranges: a contiguous column's rows are idx[lo] .. idx[lo] + len
+    const int rows_per_warp = 32 * (sizeof(Real) == 8 ? 4 : 8);
+    f_nCC = f_nCR = f_nG = f_nW = 0;
     for (SweepItem &it : p0.items) {
       const int len = it.hi - it.lo;
       const int first_row = len ? Xth.idx[it.lo] : 0;
       it.lo = first_row, it.hi = first_row + len;
+      if (len > rows_per_warp * FIELD_WARPS)
+        f_nCC++;
+      else if (len > rows_per_warp * FIELD_GROUP_WARPS)
+        f_nCR++;
+      else if (len > rows_per_warp)
+        f_nG++;
+      else
+        f_nW++;
     }
     f_items0.upload(p0.items, stream);
     f_itemsL.upload(pL.items, stream);
@@ -910,7 +921,14 @@ template <typename Real> struct Trainer : TrainerBase {
   }
 
   template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a) {
-    auto kernel = k_field_stream<Real, IS_V, UNIT, PEND>;
+    if (IS_V && f_tail > 1)
+      launch_field_stream_as<IS_V, UNIT, true, PEND>(a);
+    else
+      launch_field_stream_as<IS_V, UNIT, false, PEND>(a);
+  }
+  template <bool IS_V, bool UNIT, bool HAS_MID, int PEND>
+  void launch_field_stream_as(const FieldStreamArgs<Real> &a) {
+    auto kernel = k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND>;
     const size_t smem = 3 * static_cast<size_t>(f_tab) * sizeof(Real);
     static size_t configured = 0; // per instantiation
     if (smem > configured) {
@@ -931,10 +949,12 @@ template <typename Real> struct Trainer : TrainerBase {
     {
       FieldStreamArgs<Real> a;
       a.item = reinterpret_cast<const int4 *>(f_items0.p + f_level0.s0);
-      a.nC = f_level0.w0 - f_level0.s0, a.nW = f_level0.end - f_level0.w0;
+      a.nCC = f_nCC, a.nCR = f_nCR, a.nG = f_nG, a.nW = f_nW;
       a.sched = f_sched.p + (f_launch++);
       a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
       a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;
+      a.tail_last = f_tail_idx.p + static_cast<int64_t>(f_tail - 1) * N;
+      a.tval_last = f_tail_val.p ? f_tail_val.p + static_cast<int64_t>(f_tail - 1) * N : nullptr;
       a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
       a.last_base = f_last_base, a.n_tab = f_tab;

@@ -27,8 +27,8 @@
 namespace myfm {
 
 constexpr int FIELD_THREADS = 1024; // streaming pass: one persistent CTA per SM
-constexpr int FIELD_R = 8;          // rows per lane kept in registers between reduction and update
-constexpr int FIELD_WARP_MAX = 1024;  // longest level-0 column handled by one warp
+// rows per lane kept in registers between the reduction and the update: 8 (f32), 4 (f64)
+constexpr int FIELD_BATCH = 4;       // level-0 columns a warp takes per scheduling step
 constexpr int FIELD_CTA_MAX = 32768;  // longest level-0 column (one CTA); longer: general path
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_WARP_MAX = 256;   // last level: warp per column up to here,
@@ -37,14 +37,16 @@ constexpr int STATS_CHUNK = 8192;     // one CTA per column up to here, chunks o
 enum { PEND_NONE = 0, PEND_W = 1, PEND_V = 2 };
 
 template <typename Real> struct FieldStreamArgs {
-  const int4 *item; // level-0 columns {column, first row, end row, -}: nC CTA-wide, then nW per warp
-  int nC, nW;
+  const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
+  int nCC, nCR, nG, nW;
   int *sched;       // work counter of the warp items (zero at launch)
   Pair<Real> *eq;
   int64_t n_rows;
   int n_tail;           // L - 1
   const int *tail_idx;  // [n_tail][n_rows]: column of the row's entries 1 .. L-1
   const Real *tail_val; // [n_tail][n_rows], unused when UNIT
+  const int *tail_last;  // = tail_idx + (n_tail - 1) * n_rows: the last field
+  const Real *tval_last; // likewise
   const Real *own_val;  // [n_rows] value of the level-0 entry, unused when UNIT
   Real *theta;          // w, or column r of V (column-major)
   Real *theta_t;        // feature-major mirror: theta_t[j * t_stride], or nullptr
@@ -56,40 +58,53 @@ template <typename Real> struct FieldStreamArgs {
   const Real *pend_told, *pend_tnew; // [n_tab] draw left pending by the previous vector
 };
 
-template <typename Real, bool IS_V, bool UNIT, int PEND> struct FieldRow {
-  const FieldStreamArgs<Real> &a;
-  const Real *s_told, *s_tnew, *s_tnext;
+// U rows of the streaming pass in flight per thread: all global loads are issued first (load),
+// the shared-memory lookups and the arithmetic follow (finish) — a row's table index comes out of
+// its own load, so interleaving the two would serialise the rows on the memory latency.
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U> struct FieldBatch {
+  static constexpr bool NEED_LAST = IS_V || PEND != PEND_NONE;
+  Pair<Real> v[U];
+  int jl[U];
+  Real xl[U], x0[U];
+
+  __device__ __forceinline__ void load(const FieldStreamArgs<Real> &a, int u, int i) {
+    v[u] = __ldcg(a.eq + i);
+    jl[u] = 0, xl[u] = Real(1), x0[u] = Real(1);
+    if (NEED_LAST)
+      jl[u] = __ldcs(a.tail_last + i) - a.last_base;
+    if (!UNIT) {
+      x0[u] = __ldcs(a.own_val + i);
+      if (NEED_LAST)
+        xl[u] = __ldcs(a.tval_last + i);
+    }
+  }
 
   // Row i as the level-0 column sees it: e with the pending update applied, q = x_i . V[:, r]
-  // (IS_V) and the row's level-0 value x0.
-  __device__ __forceinline__ void operator()(int64_t i, Real theta_old, Real &e, Real &q, Real &x0) const {
-    const Pair<Real> v = __ldcg(a.eq + i);
-    const int nt = a.n_tail;
-    int jl = 0;
-    Real xl = 1;
-    if (IS_V || PEND != PEND_NONE) {
-      jl = __ldcs(a.tail_idx + static_cast<int64_t>(nt - 1) * a.n_rows + i) - a.last_base;
-      if (!UNIT)
-        xl = __ldcs(a.tail_val + static_cast<int64_t>(nt - 1) * a.n_rows + i);
-    }
-    x0 = UNIT ? Real(1) : __ldcs(a.own_val + i);
-    e = v.x, q = v.y;
+  // (IS_V; the stored q otherwise) and the row's level-0 value x0.
+  __device__ __forceinline__ void finish(const FieldStreamArgs<Real> &a, const Real *s_told, const Real *s_tnew,
+                                         const Real *s_tnext, int u, int i, Real theta_old, Real &e, Real &q,
+                                         Real &x0_out) const {
+    e = v[u].x, q = v[u].y, x0_out = x0[u];
+    const Real xlu = xl[u];
     if (PEND == PEND_V) { // FMTrainer.hpp:366-374 of the previous factor's last-level column
-      const Real told = s_told[jl], tnew = s_tnew[jl];
-      const Real h = xl * (q - xl * told);
+      const Real told = s_told[jl[u]], tnew = s_tnew[jl[u]];
+      const Real h = xlu * (q - xlu * told);
       e = e + h * (tnew - told);
     } else if (PEND == PEND_W) { // FMTrainer.hpp:240,251
-      const Real told = s_told[jl], tnew = s_tnew[jl];
-      e = (e - xl * told) + xl * tnew;
+      const Real told = s_told[jl[u]], tnew = s_tnew[jl[u]];
+      e = (e - xlu * told) + xlu * tnew;
     }
     if (IS_V) { // q_init in CSR order (FMTrainer.hpp:320)
-      Real acc = x0 * theta_old;
-      for (int k = 0; k + 1 < nt; k++) {
-        const int j = __ldcs(a.tail_idx + static_cast<int64_t>(k) * a.n_rows + i);
-        const Real x = UNIT ? Real(1) : __ldcs(a.tail_val + static_cast<int64_t>(k) * a.n_rows + i);
-        acc += x * a.theta[j];
+      Real acc = x0[u] * theta_old;
+      if (HAS_MID) {
+#pragma unroll 1
+        for (int k = 0; k + 1 < a.n_tail; k++) {
+          const int64_t off = static_cast<int64_t>(k) * a.n_rows + i;
+          const Real x = UNIT ? Real(1) : __ldcs(a.tail_val + off);
+          acc += x * a.theta[__ldcs(a.tail_idx + off)];
+        }
       }
-      acc += xl * s_tnext[jl];
+      acc += xlu * s_tnext[jl[u]];
       q = acc;
     }
   }
@@ -124,10 +139,140 @@ __device__ __forceinline__ Pair<Real> field_update(Real e, Real q, Real x0, Real
   return v;
 }
 
-template <typename Real, bool IS_V, bool UNIT, int PEND>
-__global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(FieldStreamArgs<Real> a) {
+// One pass of NT cooperating threads (t = 0 .. NT-1) over the rows [lo, hi) of a column, U rows
+// per thread in flight.  UPDATE = false: accumulates the statistics; true: writes e and q back.
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int NT, bool UPDATE>
+__device__ __forceinline__ void field_pass(const FieldStreamArgs<Real> &a, const Real *s_told,
+                                           const Real *s_tnew, const Real *s_tnext, int lo, int hi, int t,
+                                           Real theta_old, Real theta_new, Real alpha, Real &sq, Real &lin) {
+  constexpr int U = 4;
+  for (int base = lo + t; base < hi; base += U * NT) {
+    FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, U> b;
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      b.load(a, u, min(base + u * NT, hi - 1));
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = base + u * NT;
+      if (i < hi) {
+        Real e, q, x0;
+        b.finish(a, s_told, s_tnew, s_tnext, u, i, theta_old, e, q, x0);
+        if (UPDATE)
+          __stcg(a.eq + i, field_update<Real, IS_V>(e, q, x0, theta_old, theta_new));
+        else
+          field_stats<Real, IS_V>(e, q, x0, theta_old, alpha, sq, lin);
+      }
+    }
+  }
+}
+
+constexpr int FIELD_WARPS = FIELD_THREADS / 32;
+constexpr int FIELD_GROUP_WARPS = 4; // medium columns: groups of four warps
+
+// (sq, lin) summed over the GW warps that share a column.  GW = 1: the warp alone; FIELD_GROUP_WARPS:
+// a 128-thread group with its own named barrier; FIELD_WARPS: the CTA.  Warp partials are added in
+// warp order (deterministic).  `parity` alternates between a group's consecutive columns, so one
+// barrier per column is enough.
+template <typename Real, int GW>
+__device__ __forceinline__ void field_group_sum(Real &sq, Real &lin, Real *s_part, int parity, int grp, int wig,
+                                                int lane) {
+  sq = warp_sum(sq);
+  lin = warp_sum(lin);
+  if (GW == 1)
+    return;
+  Real *buf = s_part + ((parity * (FIELD_WARPS / GW) + grp) * GW) * 2;
+  if (lane == 0)
+    buf[2 * wig] = sq, buf[2 * wig + 1] = lin;
+  if (GW == FIELD_WARPS)
+    __syncthreads();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(GW * 32) : "memory");
+  Real s = 0, l = 0;
+#pragma unroll
+  for (int w = 0; w < GW; w++)
+    s += buf[2 * w], l += buf[2 * w + 1];
+  sq = s, lin = l;
+}
+
+// A column of at most 32 * GW * NS rows handled by GW warps (thread t of the group): the rows stay
+// in registers between the reduction and the update, so every row is read once and written once.
+// FULL: slots 0 .. NS-2 hold a row in every thread (the caller picked NS = ceil(rows / threads)),
+// only the last slot is ragged; otherwise every slot is checked.
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int GW, int NS, bool FULL>
+__device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a, const Real *s_told,
+                                                  const Real *s_tnew, const Real *s_tnext, int4 it, int t,
+                                                  Real theta_old, Real alpha, Real lam, Real mu, Real z,
+                                                  Real *s_part, int parity, int grp, int wig, int lane) {
+  constexpr int NT = 32 * GW;
+  FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, NS> b;
+  Real e[NS], q[NS], x0[NS];
+  const int i0 = it.y + t;
+  bool ok[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    ok[s] = (FULL && s < NS - 1) || i0 + NT * s < it.z;
+    b.load(a, s, ok[s] ? i0 + NT * s : it.z - 1);
+  }
+  Real sq = 0, lin = 0;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    b.finish(a, s_told, s_tnew, s_tnext, s, i0 + NT * s, theta_old, e[s], q[s], x0[s]);
+    if (ok[s])
+      field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
+  }
+  field_group_sum<Real, GW>(sq, lin, s_part, parity, grp, wig, lane);
+  const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+#pragma unroll
+  for (int s = 0; s < NS; s++)
+    if (ok[s])
+      __stcg(a.eq + i0 + NT * s, field_update<Real, IS_V>(e[s], q[s], x0[s], theta_old, theta_new));
+  return theta_new;
+}
+
+// Picks the instantiation for the column's slot count (warp-uniform switch).
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int GW>
+__device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real> &a, const Real *s_told,
+                                                      const Real *s_tnew, const Real *s_tnext, int4 it, int t,
+                                                      Real theta_old, Real alpha, Real lam, Real mu, Real z,
+                                                      Real *s_part, int parity, int grp, int wig, int lane) {
+  constexpr int R = sizeof(Real) == 8 ? 4 : 8, NT = 32 * GW;
+  const int n_slots = (it.z - it.y + NT - 1) / NT;
+#define MYFM_SLOTS(NS)                                                                             \
+  case NS:                                                                                         \
+    return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, GW, (NS <= R ? NS : R), true>(                       \
+        a, s_told, s_tnew, s_tnext, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane);
+  switch (n_slots) {
+    MYFM_SLOTS(1)
+    MYFM_SLOTS(2)
+    MYFM_SLOTS(3)
+    MYFM_SLOTS(4)
+    MYFM_SLOTS(5)
+    MYFM_SLOTS(6)
+    MYFM_SLOTS(7)
+    MYFM_SLOTS(8)
+  }
+#undef MYFM_SLOTS
+  // empty column (one warp): the draw comes from the prior alone
+  return column_draw<Real, IS_V>(Real(0), Real(0), theta_old, alpha, lam, mu, z);
+}
+
+template <typename Real>
+__device__ __forceinline__ void field_store_theta(const FieldStreamArgs<Real> &a, int j, Real theta_new) {
+  a.theta[j] = theta_new;
+  if (a.theta_t)
+    a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+}
+
+// Level-0 columns by length (items are sorted longest first; R = 8 rows per thread in f32, 4 in f64):
+//   nCC  longer than 32 R FIELD_WARPS rows: the whole CTA, two passes (the second re-reads through L2)
+//   nCR  up to 32 R FIELD_WARPS rows:       the whole CTA, rows in registers
+//   nG   up to 32 R FIELD_GROUP_WARPS rows: a group of four warps, rows in registers
+//   nW   up to 32 R rows:                   one warp, rows in registers, handed out dynamically
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND>
+__global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_constant__ FieldStreamArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ Real scratch[32];
+  __shared__ Real s_part_cta[2 * FIELD_WARPS * 2], s_part_grp[2 * FIELD_WARPS * 2];
   Real *s_told = reinterpret_cast<Real *>(s_raw), *s_tnew = s_told + a.n_tab, *s_tnext = s_tnew + a.n_tab;
   for (int t = threadIdx.x; t < a.n_tab; t += FIELD_THREADS) {
     if (PEND != PEND_NONE)
@@ -136,106 +281,88 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(FieldStreamAr
       s_tnext[t] = a.theta[a.last_base + t];
   }
   __syncthreads();
-  const FieldRow<Real, IS_V, UNIT, PEND> row{a, s_told, s_tnew, s_tnext};
   const Real alpha = *a.alpha;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // long columns: the whole CTA, two passes over the rows (the second re-reads through L2)
-  for (int c = blockIdx.x; c < a.nC; c += gridDim.x) {
+  for (int c = blockIdx.x; c < a.nCC; c += gridDim.x) {
     const int4 it = __ldg(a.item + c);
     const int j = it.x;
     const Real theta_old = a.theta[j];
     const int g = a.group[j];
     const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
     Real sq = 0, lin = 0;
-    for (int64_t i = it.y + threadIdx.x; i < it.z; i += FIELD_THREADS) {
-      Real e, q, x0;
-      row(i, theta_old, e, q, x0);
-      field_stats<Real, IS_V>(e, q, x0, theta_old, alpha, sq, lin);
-    }
+    field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+                                                                      threadIdx.x, theta_old, theta_old, alpha, sq, lin);
     sq = block_sum(sq, scratch);
     lin = block_sum(lin, scratch);
     const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
-    for (int64_t i = it.y + threadIdx.x; i < it.z; i += FIELD_THREADS) {
-      Real e, q, x0;
-      row(i, theta_old, e, q, x0);
-      __stcg(a.eq + i, field_update<Real, IS_V>(e, q, x0, theta_old, theta_new));
-    }
+    field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+                                                                     threadIdx.x, theta_old, theta_new, alpha, sq, lin);
     __syncthreads(); // every thread has read theta[j]
-    if (threadIdx.x == 0) {
-      a.theta[j] = theta_new;
-      if (a.theta_t)
-        a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+    if (threadIdx.x == 0)
+      field_store_theta(a, j, theta_new);
+  }
+
+  {
+    int parity = 0;
+    for (int c = blockIdx.x; c < a.nCR; c += gridDim.x, parity ^= 1) {
+      const int4 it = __ldg(a.item + a.nCC + c);
+      const int j = it.x;
+      const Real theta_old = a.theta[j];
+      const int g = a.group[j];
+      const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+      constexpr int R = sizeof(Real) == 8 ? 4 : 8;
+      const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_WARPS, R, false>(
+          a, s_told, s_tnew, s_tnext, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane);
+      if (threadIdx.x == 0) // every thread read theta[j] before the barrier of the reduction
+        field_store_theta(a, j, theta_new);
     }
   }
 
-  // the rest: one warp per column, longest first, handed out through a counter
-  int k = 0;
-  if (lane == 0)
-    k = atomicAdd(a.sched, 1);
-  k = __shfl_sync(FULL_MASK, k, 0);
-  while (k < a.nW) {
-    int k_next = 0;
-    if (lane == 0)
-      k_next = atomicAdd(a.sched, 1);
-    const int4 it = __ldg(a.item + a.nC + k);
-    const int j = it.x, n = it.z - it.y;
-    const Real theta_old = a.theta[j];
-    const int g = a.group[j];
-    const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
-    Real sq = 0, lin = 0;
-    if (n <= 32 * FIELD_R) { // rows stay in registers between the reduction and the update
-      Real e[FIELD_R], q[FIELD_R], x0[FIELD_R];
-      const int n_slots = (n + 31) >> 5;
-#pragma unroll
-      for (int s = 0; s < FIELD_R; s++) {
-        e[s] = 0, q[s] = 0, x0[s] = 0;
-        if (s < n_slots) {
-          const int i = it.y + lane + 32 * s;
-          if (i < it.z)
-            row(i, theta_old, e[s], q[s], x0[s]);
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < FIELD_R; s++)
-        if (s < n_slots && it.y + lane + 32 * s < it.z)
-          field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
-      sq = warp_sum(sq);
-      lin = warp_sum(lin);
-      const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
-#pragma unroll
-      for (int s = 0; s < FIELD_R; s++)
-        if (s < n_slots) {
-          const int i = it.y + lane + 32 * s;
-          if (i < it.z)
-            __stcg(a.eq + i, field_update<Real, IS_V>(e[s], q[s], x0[s], theta_old, theta_new));
-        }
-      if (lane == 0) {
-        a.theta[j] = theta_new;
-        if (a.theta_t)
-          a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
-      }
-    } else {
-      for (int64_t i = it.y + lane; i < it.z; i += 32) {
-        Real e, q, x0;
-        row(i, theta_old, e, q, x0);
-        field_stats<Real, IS_V>(e, q, x0, theta_old, alpha, sq, lin);
-      }
-      sq = warp_sum(sq);
-      lin = warp_sum(lin);
-      const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
-      for (int64_t i = it.y + lane; i < it.z; i += 32) {
-        Real e, q, x0;
-        row(i, theta_old, e, q, x0);
-        __stcg(a.eq + i, field_update<Real, IS_V>(e, q, x0, theta_old, theta_new));
-      }
-      if (lane == 0) {
-        a.theta[j] = theta_new;
-        if (a.theta_t)
-          a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
-      }
+  {
+    constexpr int GROUPS = FIELD_WARPS / FIELD_GROUP_WARPS;
+    const int grp = warp / FIELD_GROUP_WARPS, wig = warp % FIELD_GROUP_WARPS;
+    int parity = 0;
+    for (int k = blockIdx.x + gridDim.x * grp; k < a.nG; k += gridDim.x * GROUPS, parity ^= 1) {
+      const int4 it = __ldg(a.item + a.nCC + a.nCR + k);
+      const int j = it.x;
+      const Real theta_old = a.theta[j];
+      const int g = a.group[j];
+      const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_GROUP_WARPS>(
+          a, s_told, s_tnew, s_tnext, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
+          lane);
+      if (wig == 0 && lane == 0)
+        field_store_theta(a, j, theta_new);
     }
-    k = __shfl_sync(FULL_MASK, k_next, 0);
+  }
+
+  // One warp per column.  The first batch of FIELD_BATCH columns is static, the following ones are
+  // handed out through a counter (one atomic per batch: same-address atomics retire at about one
+  // per two cycles chip-wide, one per column would bound the kernel).
+  const int total_warps = gridDim.x * FIELD_WARPS;
+  const int4 *items_w = a.item + a.nCC + a.nCR + a.nG;
+  int kb = (blockIdx.x + gridDim.x * warp) * FIELD_BATCH; // longest columns spread over the SMs
+  while (kb < a.nW) {
+    int kb_next = 0;
+    if (lane == 0)
+      kb_next = total_warps * FIELD_BATCH + atomicAdd(a.sched, FIELD_BATCH);
+    const int k_end = min(kb + FIELD_BATCH, a.nW);
+    int4 it_next = __ldg(items_w + kb);
+    for (int k = kb; k < k_end; k++) {
+      const int4 it = it_next;
+      if (k + 1 < k_end)
+        it_next = __ldg(items_w + k + 1);
+      const int j = it.x;
+      const Real theta_old = a.theta[j];
+      const int g = a.group[j];
+      const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, 1>(
+          a, s_told, s_tnew, s_tnext, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane);
+      if (lane == 0)
+        field_store_theta(a, j, theta_new);
+    }
+    kb = __shfl_sync(FULL_MASK, kb_next, 0);
   }
 }
 
