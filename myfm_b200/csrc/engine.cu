@@ -377,11 +377,14 @@ template <typename Real> struct Trainer : TrainerBase {
   // device-side mt19937 stream (regression; mt_device.cuh): runs one sweep ahead on its own stream
   bool device_rng = false;
   cudaStream_t rng_stream = nullptr;
-  DevBuf<MtDeviceState> mt_state;
-  DevBuf<int> mt_error;
+  DevBuf<MtControl> mt_ctl;
+  DevBuf<uint32_t> mt_ring;      // tempered words of the stream, ring[n & mt_mask]
+  unsigned long long mt_mask = 0, mt_ahead = 0;
+  int mt_final_stage = 0;
+  DevBuf<int> mt_tile_count;
+  DevBuf<long long> mt_tile_offset;
   DevBuf<Real> mt_consts; // a1[G+1], a2[G+1]
   DevBuf<Real> z_slot[2];
-  DevBuf<Real> z_raw; // (y, r2) of every bulk normal of the sweep being generated
   cudaEvent_t z_ready[2] = {nullptr, nullptr}, z_free[2] = {nullptr, nullptr};
   int64_t gen_index = 0;
   const Real *z_last = nullptr;
@@ -673,16 +676,42 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     for (auto &zb : z_slot)
       zb.alloc(layout.total);
-    z_raw.alloc(2 * static_cast<size_t>(layout.total));
     // hand the generator over where create_FM left it: operator<< prints x[0..623] and p
     std::ostringstream os;
     os << rng.gen;
     std::istringstream is(os.str());
-    std::vector<MtDeviceState> st(1);
-    for (int i = 0; i < MT_N; i++)
-      is >> st[0].x[i];
-    is >> st[0].p;
-    mt_state.upload(st, stream);
+    std::vector<MtControl> ctl(1);
+    std::memset(&ctl[0], 0, sizeof(MtControl));
+    std::vector<uint32_t> first_words(MT_N);
+    for (int i = 0; i < MT_N; i++) {
+      is >> ctl[0].window[i];
+      first_words[i] = mt_temper(ctl[0].window[i]);
+    }
+    unsigned long long p = 0;
+    is >> p;
+    ctl[0].produced = MT_N;
+    // words one sweep consumes at most: every bulk segment is given 1 % + 4096 attempts more than
+    // its expectation (acceptance pi/4; the standard deviation is below 0.05 % beyond 1e6
+    // attempts), every scalar draw a budget of 64 words
+    constexpr int WPA = MtTraits<Real>::WPA;
+    const long long n_scalar = 2 + 2 * static_cast<long long>(G) * (K + 1);
+    const long long need = (bulk_attempts(D_all) + bulk_attempts(static_cast<long long>(K) * D_all)) * WPA +
+                           64 * n_scalar + MT_SCALAR_WINDOW;
+    mt_ahead = static_cast<unsigned long long>(need);
+    unsigned long long cap = 1 << 16;
+    while (cap < 2 * mt_ahead + 4 * MT_N)
+      cap <<= 1;
+    mt_mask = cap - 1;
+    mt_ring.alloc(cap);
+    mt_ring.upload(first_words.data(), MT_N, stream);
+    // stages of a sweep: head scalars, w bulk, V-hyper scalars, V bulk (absent ones are skipped)
+    mt_final_stage = 1 + (layout.z_w >= 0 && D_all > 0 ? 1 : 0) + (G > 0 && K > 0 ? 1 : 0) +
+                     (K > 0 && D_all > 0 ? 1 : 0);
+    ctl[0].pos[mt_final_stage] = p;
+    mt_ctl.upload(ctl, stream);
+    const long long max_tiles = ceil_div(bulk_attempts(static_cast<long long>(std::max(K, 1)) * D_all), MT_BULK_TILE);
+    mt_tile_count.alloc(max_tiles + 1);
+    mt_tile_offset.alloc(max_tiles + 2);
     // gamma_distribution::param_type::_M_initialize (bits/random.tcc:2338-2345), shape >= 1
     std::vector<Real> consts(2 * (G + 1));
     for (int g = 0; g <= G; g++) {
@@ -692,9 +721,30 @@ template <typename Real> struct Trainer : TrainerBase {
       consts[G + 1 + g] = Real(1.0) / std::sqrt(Real(9.0) * a1);
     }
     mt_consts.upload(consts, stream);
-    mt_error.alloc(1);
-    mt_error.zero(stream);
     MYFM_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // polar attempts examined for `count` bulk normals (mt_device.cuh)
+  static long long bulk_attempts(long long count) {
+    if (count <= 0)
+      return 0;
+    const long long a = static_cast<long long>(std::ceil(count * 1.2733 * 1.01)) + 4096;
+    return (a + MT_BULK_TILE - 1) / MT_BULK_TILE * MT_BULK_TILE;
+  }
+
+  void launch_bulk(int &stage, long long count, Real *out, long long out0) {
+    if (count <= 0)
+      return;
+    const long long n_attempts = bulk_attempts(count);
+    const int n_tiles = static_cast<int>(n_attempts / MT_BULK_TILE);
+    k_mt_bulk_count<Real><<<n_tiles, MT_BULK_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, stage, n_attempts,
+                                                                        mt_tile_count.p);
+    k_mt_bulk_scan<<<1, 1024, 0, rng_stream>>>(n_tiles, mt_tile_count.p, mt_tile_offset.p);
+    k_mt_bulk_emit<Real><<<n_tiles, MT_BULK_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, stage, stage + 1,
+                                                                       n_attempts, count, mt_tile_offset.p, n_tiles, out,
+                                                                       out0);
+    launched(3);
+    stage++;
   }
 
   void launch_variates(int64_t index) {
@@ -702,32 +752,57 @@ template <typename Real> struct Trainer : TrainerBase {
     if (index >= 2)
       MYFM_CUDA(cudaStreamWaitEvent(rng_stream, z_free[slot], 0));
     const SweepLayout &L = layout;
-    MtProgram prog;
-    prog.g_alpha = L.g_alpha, prog.z_w0 = L.z_w0, prog.g_lw = L.g_lw, prog.z_mw = L.z_mw;
-    prog.z_w = L.z_w, prog.g_lV = L.g_lV, prog.z_mV = L.z_mV, prog.z_V = L.z_V;
-    prog.G = G, prog.K = K, prog.dim_all = D_all;
-    prog.a1 = mt_consts.p, prog.a2 = mt_consts.p + (G + 1);
-    k_mt_sweep_variates<Real><<<1, MT_THREADS, 0, rng_stream>>>(mt_state.p, prog, z_slot[slot].p, z_raw.p,
-                                                                mt_error.p);
-    const long long n0 = L.z_w >= 0 ? D_all : 0, n1 = static_cast<long long>(K) * D_all;
-    if (n0 + n1) {
-      k_mt_finish_normals<Real><<<ceil_div(n0 + n1, 256), 256, 0, rng_stream>>>(
-          z_raw.p, z_slot[slot].p, L.z_w >= 0 ? L.z_w : 0, n0, L.z_V, n1);
+    Real *out = z_slot[slot].p;
+    k_mt_generate<<<1, MT_GEN_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, mt_ahead, mt_final_stage);
+    launched();
+    int stage = 0;
+    { // alpha, w0, lambda_w, mu_w
+      MtScalarProgram prog;
+      prog.a1 = mt_consts.p, prog.a2 = mt_consts.p + (G + 1);
+      int n = 0;
+      if (L.g_alpha >= 0)
+        prog.seg[n++] = MtScalarSegment{1, 1, L.g_alpha, G, 0};
+      if (L.z_w0 >= 0)
+        prog.seg[n++] = MtScalarSegment{0, 1, L.z_w0, 0, 0};
+      if (G > 0) {
+        prog.seg[n++] = MtScalarSegment{1, G, L.g_lw, 0, G};
+        prog.seg[n++] = MtScalarSegment{0, G, L.z_mw, 0, 0};
+      }
+      prog.n_segments = n;
+      k_mt_scalars<Real><<<1, MT_SCALAR_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, stage, stage + 1, prog,
+                                                                   out);
       launched();
+      stage++;
     }
+    if (L.z_w >= 0)
+      launch_bulk(stage, D_all, out, L.z_w);
+    if (G > 0 && K > 0) { // lambda_V (factor-major, group-minor), then mu_V
+      MtScalarProgram prog;
+      prog.a1 = mt_consts.p, prog.a2 = mt_consts.p + (G + 1);
+      prog.seg[0] = MtScalarSegment{1, K * G, L.g_lV, 0, G};
+      prog.seg[1] = MtScalarSegment{0, K * G, L.z_mV, 0, 0};
+      prog.n_segments = 2;
+      k_mt_scalars<Real><<<1, MT_SCALAR_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, stage, stage + 1, prog,
+                                                                   out);
+      launched();
+      stage++;
+    }
+    launch_bulk(stage, static_cast<long long>(K) * D_all, out, L.z_V);
+    if (stage != mt_final_stage)
+      throw std::logic_error("device RNG: stage count mismatch.");
     MYFM_CUDA(cudaGetLastError());
     MYFM_CUDA(cudaEventRecord(z_ready[slot], rng_stream));
-    launched();
   }
 
   void check_rng_error() {
     if (!device_rng)
       return;
     int err = 0;
-    MYFM_CUDA(cudaMemcpyAsync(&err, mt_error.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MYFM_CUDA(cudaMemcpyAsync(&err, &mt_ctl.p->error, sizeof(int), cudaMemcpyDeviceToHost, stream));
     MYFM_CUDA(cudaStreamSynchronize(stream));
     if (err)
-      throw std::runtime_error("device mt19937 stream ran dry inside one draw (set MYFM_HOST_RNG=1).");
+      throw std::runtime_error("device mt19937 stream: the word ring ran dry or a bulk segment found too few accepted "
+                               "attempts (set MYFM_HOST_RNG=1).");
   }
 
   // Standardised variates of one sweep, in the reference's consumption order.

@@ -11,11 +11,15 @@
 // for double; bits/random.tcc generate_canonical), so "the k-th normal" is "the k-th accepted
 // attempt": an acceptance flag per attempt, a prefix sum, and a compaction.
 //
-// One CTA runs the whole program: it regenerates MT19937 blocks of 624 words in shared memory
-// (3 barriers per block, tempering fused), lets thread 0 interpret the few scalar draws of a
-// sweep, and compacts the accepted attempts of the bulk normals cooperatively; the log/sqrt of
-// the polar method then runs as an ordinary data-parallel kernel.  Both run on their own stream
-// one sweep ahead of the sampler.
+// Split in two so that only the inherently serial part is serial:
+//   k_mt_generate   ONE CTA extends the raw word stream into a ring buffer in global memory.
+//                   x[n] = x[n-227] ^ twist(x[n-624], x[n-623]): 227 words per round are
+//                   independent, one barrier per round, tempering fused into the store.
+//   consumers       read the ring at a stream position kept on the device:
+//                   k_mt_scalars (the few scalar draws of a sweep, one thread, a shared-memory
+//                   window of the ring) and k_mt_bulk_count / _scan / _emit (the bulk normals,
+//                   data parallel over all SMs, log/sqrt fused into the compaction).
+// All of it runs on its own stream one sweep ahead of the sampler.
 //
 // Arithmetic follows bits/random.tcc (normal_distribution::operator() :1811-1846,
 // gamma_distribution::operator() :2355-2393, generate_canonical :3349-3385) including the
@@ -31,25 +35,19 @@
 namespace myfm {
 
 constexpr int MT_N = 624, MT_M = 397;
-constexpr int MT_THREADS = 256;
-constexpr int MT_BUF_BLOCKS = 10;                 // shared word buffer capacity, in MT blocks
-constexpr int MT_BUF_WORDS = MT_BUF_BLOCKS * MT_N;
+constexpr int MT_LAG = MT_N - MT_M;   // 227 words per round are independent of each other
+constexpr int MT_WINDOW = 1024;       // circular window of the untempered recurrence (power of two)
+constexpr int MT_GEN_THREADS = 256;
+constexpr int MT_MAX_STAGES = 8;
 
-// Persistent generator state in global memory: x[624] untempered words + p (next word index,
-// 624 = regenerate first) — the layout std::mt19937 streams out with operator<<.
-struct MtDeviceState {
-  uint32_t x[MT_N];
-  uint32_t p;
-};
-
-// Where the standardised variates of one regression sweep go (rng.hpp: SweepLayout) and the
-// shape-dependent gamma constants, computed on the host exactly as libstdc++ does.
-struct MtProgram {
-  long long g_alpha, z_w0, g_lw, z_mw, z_w, g_lV, z_mV, z_V; // offsets, -1 = not drawn
-  int G, K;
-  long long dim_all;
-  const void *a1;  // [G + 1] Real: _M_malpha - 1/3 per group, then alpha's
-  const void *a2;  // [G + 1] Real: 1 / sqrt(9 a1)
+// Stream positions count words from the start of the device stream ("window coordinates": the
+// 624 state words handed over by the host are words 0 .. 623, of which the first `p` were already
+// consumed there).  ring[n & mask] = tempered word n.
+struct MtControl {
+  uint32_t window[MT_WINDOW];       // untempered word n at window[n % MT_WINDOW], last 624 valid
+  unsigned long long produced;      // words generated so far
+  unsigned long long pos[MT_MAX_STAGES]; // consumer position after each stage of a sweep
+  int error;                        // 1: the ring ran dry, 2: not enough accepted attempts
 };
 
 template <typename Real> struct MtTraits;
@@ -60,7 +58,7 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
   return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
-__device__ __forceinline__ uint32_t mt_temper(uint32_t z) {
+__host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t z) {
   z ^= (z >> 11);
   z ^= (z << 7) & 0x9d2c5680u;
   z ^= (z << 15) & 0xefc60000u;
@@ -83,7 +81,7 @@ __device__ __forceinline__ double mt_canonical(const uint32_t *w, double) {
 __device__ __forceinline__ float mt_log(float x) { return static_cast<float>(log(static_cast<double>(x))); }
 __device__ __forceinline__ double mt_log(double x) { return log(x); }
 
-// One polar attempt of normal_distribution::operator() starting at words w[0 .. WPA).
+// One polar attempt of normal_distribution::operator() on the words w[0 .. WPA).
 // Returns true when accepted; x, y, r2 as in the reference.
 template <typename Real>
 __device__ __forceinline__ bool mt_polar(const uint32_t *w, Real &x, Real &y, Real &r2) {
@@ -97,98 +95,86 @@ template <typename Real> __device__ __forceinline__ Real mt_polar_mult(Real r2) 
   return sqrt(-2 * mt_log(r2) / r2);
 }
 
-template <typename Real> struct MtCta {
-  uint32_t *cur, *prev; // [624] each: untempered state of the last two generated blocks
-  uint32_t *buf;        // [MT_BUF_WORDS] tempered words not yet consumed: buf[head .. head+avail)
-  int *ctl;             // [0] head, [1] avail (scalar-phase hand-off), [3] error, [4..5] round scratch
-  int *warp_tot;        // [32]
-  // Uniform per-thread copies: every thread tracks the buffer window itself, so appending a block
-  // needs no bookkeeping barrier.  Thread 0 alone moves them during a scalar draw and publishes
-  // the result through ctl[0..1].
-  int head = 0, avail = 0, last = 0; // last = size of the most recently appended block
+// ------------------------------------------------------------------------------------------------
+// The serial part: extend the word stream until `ahead` words lie beyond the consumer position.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MT_GEN_THREADS)
+    k_mt_generate(MtControl *ctl, uint32_t *__restrict__ ring, unsigned long long mask,
+                  unsigned long long ahead, int final_stage) {
+  __shared__ uint32_t W[MT_WINDOW];
+  const int t = threadIdx.x;
+  for (int i = t; i < MT_WINDOW; i += MT_GEN_THREADS)
+    W[i] = ctl->window[i];
+  const unsigned long long consumed = ctl->pos[final_stage];
+  unsigned long long m = ctl->produced;
+  __syncthreads();
+  if (t == 0)
+    ctl->pos[0] = consumed; // the next sweep starts where the last one stopped
+  const unsigned long long goal = consumed + ahead;
+  long long rounds = goal > m ? static_cast<long long>((goal - m + MT_LAG - 1) / MT_LAG) : 0;
+  // thread t of round r produces word m + t; x[n-227] is the word this thread produced one round
+  // earlier, the other two operands were produced at least two rounds earlier by other threads,
+  // so one barrier per round orders everything.
+  uint32_t prev = 0;
+  if (t < MT_LAG)
+    prev = W[(m + t - MT_LAG) & (MT_WINDOW - 1)];
+  for (long long r = 0; r < rounds; r++) {
+    if (t < MT_LAG) {
+      const unsigned long long n = m + t;
+      const uint32_t v = prev ^ mt_twist(W[(n - MT_N) & (MT_WINDOW - 1)], W[(n - MT_N + 1) & (MT_WINDOW - 1)]);
+      W[n & (MT_WINDOW - 1)] = v;
+      ring[n & mask] = mt_temper(v);
+      prev = v;
+    }
+    m += MT_LAG;
+    __syncthreads();
+  }
+  for (int i = t; i < MT_WINDOW; i += MT_GEN_THREADS)
+    ctl->window[i] = W[i];
+  if (t == 0)
+    ctl->produced = m;
+}
 
-  // Moves the unconsumed words to the front of the buffer.  All threads; ends with a barrier.
-  __device__ void compact() {
-    if (head == 0)
-      return;
-    const int h = head, n = avail;
-    // forward copy in chunks of blockDim: a chunk is read completely before it is written
-    for (int base = 0; base < n; base += blockDim.x) {
-      const int i = base + threadIdx.x;
-      uint32_t v = 0;
-      if (i < n)
-        v = buf[h + i];
-      __syncthreads();
-      if (i < n)
-        buf[i] = v;
-    }
-    head = 0;
-    __syncthreads();
-  }
+// ------------------------------------------------------------------------------------------------
+// Scalar draws.  One CTA; thread 0 interprets the stream out of a shared-memory window of the
+// ring that all threads refill between draws (words beyond the window are read from the ring
+// directly: a draw that needs more than MT_SCALAR_RESERVE words has probability < 1e-30).
+// ------------------------------------------------------------------------------------------------
+constexpr int MT_SCALAR_THREADS = 128;
+constexpr int MT_SCALAR_WINDOW = 4096;
+constexpr int MT_SCALAR_RESERVE = 256;
 
-  // Appends the rest of the state block the kernel starts with.
-  __device__ void append_initial(uint32_t p) {
-    const int n = MT_N - static_cast<int>(p);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      buf[head + avail + i] = mt_temper(cur[p + i]);
-    avail += n, last = n;
-    __syncthreads();
-  }
-  // Regenerates the next block of 624 words (three barriers) and appends its tempered words.
-  __device__ void append_block() {
-    uint32_t *x = cur, *y = prev; // y becomes the new block; the roles swap at the end
-    const int t = threadIdx.x;
-    uint32_t *out = buf + head + avail;
-    if (t < MT_N - MT_M) { // [0, 227)
-      uint32_t v = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
-      y[t] = v, out[t] = mt_temper(v);
-    }
-    __syncthreads();
-    if (t < MT_N - MT_M) { // [227, 454)
-      const int i = t + (MT_N - MT_M);
-      uint32_t v = y[i - (MT_N - MT_M)] ^ mt_twist(x[i], x[i + 1]);
-      y[i] = v, out[i] = mt_temper(v);
-    }
-    __syncthreads();
-    {
-      const int i = t + 2 * (MT_N - MT_M); // [454, 624)
-      if (i < MT_N - 1) {
-        uint32_t v = y[i - (MT_N - MT_M)] ^ mt_twist(x[i], x[i + 1]);
-        y[i] = v, out[i] = mt_temper(v);
-      } else if (i == MT_N - 1) {
-        uint32_t v = y[MT_M - 1] ^ mt_twist(x[MT_N - 1], y[0]);
-        y[i] = v, out[i] = mt_temper(v);
-      }
-    }
-    __syncthreads();
-    avail += MT_N, last = MT_N;
-    cur = y, prev = x;
-  }
-  // Makes at least `need` words available (need <= 624).  Uniform across the CTA.
-  __device__ void ensure(int need) {
-    if (avail >= need)
-      return;
-    if (head + avail + MT_N > MT_BUF_WORDS)
-      compact();
-    append_block();
-  }
-  // Fills the buffer to capacity (bulk phase).
-  __device__ void fill() {
-    compact();
-    while (avail + MT_N <= MT_BUF_WORDS)
-      append_block();
-  }
+struct MtScalarSegment {
+  int kind;          // 0 = fresh normal, 1 = gamma
+  int count;
+  long long out0;    // variate i of the segment goes to out[out0 + i]
+  int shape_base, shape_mod; // gamma constants index: shape_base + (shape_mod ? i % shape_mod : 0)
+};
+struct MtScalarProgram {
+  int n_segments;
+  MtScalarSegment seg[4];
+  const void *a1; // Real: _M_malpha - 1/3 per shape
+  const void *a2; // Real: 1 / sqrt(9 a1)
+};
 
-  // ---- scalar draws (thread 0 only; at least 624 words available) ------------------------------
-  __device__ bool take(int n, const uint32_t *&w) {
-    if (avail < n) {
-      ctl[3] = 1; // ran dry inside one draw: p < 1e-90, reported to the host
-      w = buf;
-      return false;
-    }
-    w = buf + head;
-    head += n, avail -= n;
-    return true;
+template <typename Real> struct MtReader {
+  const uint32_t *ring;
+  unsigned long long mask, produced;
+  const uint32_t *win;
+  unsigned long long win_lo, win_hi;
+  unsigned long long pos;
+  int error = 0;
+
+  __device__ uint32_t word(unsigned long long n) const {
+    return (n >= win_lo && n < win_hi) ? win[n - win_lo] : ring[n & mask];
+  }
+  template <int NW> __device__ void take(uint32_t (&w)[NW]) {
+    if (pos + NW > produced)
+      error = 1;
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+      w[i] = word(pos + i);
+    pos += NW;
   }
   struct Normal { // std::normal_distribution<Real>(0, 1)
     bool saved_available = false;
@@ -200,11 +186,10 @@ template <typename Real> struct MtCta {
       return nd.saved;
     }
     Real x, y, r2;
-    const uint32_t *w;
+    uint32_t w[MtTraits<Real>::WPA];
     do {
-      if (!take(MtTraits<Real>::WPA, w))
-        return 0;
-    } while (!mt_polar<Real>(w, x, y, r2));
+      take(w);
+    } while (!mt_polar<Real>(w, x, y, r2) && !error);
     const Real mult = mt_polar_mult(r2);
     nd.saved = x * mult, nd.saved_available = true;
     return y * mult;
@@ -213,16 +198,17 @@ template <typename Real> struct MtCta {
   __device__ Real gamma(Real a1, Real a2) {
     Normal nd;
     Real u, v, n;
-    const uint32_t *w;
+    uint32_t w[MtTraits<Real>::WPA / 2];
     for (;;) {
       do {
         n = normal(nd);
         v = Real(1.0) + a2 * n;
-      } while (v <= 0.0 && !ctl[3]);
+      } while (v <= 0.0 && !error);
       v = v * v * v;
-      if (!take(MtTraits<Real>::WPA / 2, w))
-        return 0;
+      take(w);
       u = mt_canonical(w, Real());
+      if (error)
+        break;
       // the literals below are double in the reference: these expressions are double arithmetic
       const double nn = static_cast<double>(n), vv = static_cast<double>(v);
       if (!(static_cast<double>(u) > static_cast<double>(Real(1.0)) - 0.0331 * nn * nn * nn * nn))
@@ -233,158 +219,188 @@ template <typename Real> struct MtCta {
     }
     return a1 * v;
   }
-  // One scalar draw by thread 0 (kind 0 = fresh normal, 1 = gamma); all threads call.
-  __device__ void scalar(int kind, Real a1, Real a2, Real *dst) {
-    ensure(MT_N);
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(MT_SCALAR_THREADS)
+    k_mt_scalars(MtControl *ctl, const uint32_t *__restrict__ ring, unsigned long long mask, int stage_in,
+                 int stage_out, MtScalarProgram prog, Real *__restrict__ out) {
+  __shared__ uint32_t win[MT_SCALAR_WINDOW];
+  __shared__ unsigned long long s_pos;
+  __shared__ int s_seg, s_i, s_done;
+  if (threadIdx.x == 0)
+    s_pos = ctl->pos[stage_in], s_seg = 0, s_i = 0, s_done = 0;
+  __syncthreads();
+  const Real *a1 = static_cast<const Real *>(prog.a1), *a2 = static_cast<const Real *>(prog.a2);
+  while (!s_done) {
+    const unsigned long long lo = s_pos;
+    for (int i = threadIdx.x; i < MT_SCALAR_WINDOW; i += MT_SCALAR_THREADS)
+      win[i] = ring[(lo + i) & mask];
+    __syncthreads();
     if (threadIdx.x == 0) {
-      Normal nd;
-      *dst = kind == 0 ? normal(nd) : gamma(a1, a2);
-      ctl[0] = head, ctl[1] = avail;
+      MtReader<Real> rd;
+      rd.ring = ring, rd.mask = mask, rd.produced = ctl->produced;
+      rd.win = win, rd.win_lo = lo, rd.win_hi = lo + MT_SCALAR_WINDOW, rd.pos = lo;
+      int seg = s_seg, i = s_i;
+      while (seg < prog.n_segments && rd.pos + MT_SCALAR_RESERVE <= rd.win_hi) {
+        const MtScalarSegment &sg = prog.seg[seg];
+        if (i >= sg.count) {
+          seg++, i = 0;
+          continue;
+        }
+        Real v;
+        if (sg.kind == 0) {
+          typename MtReader<Real>::Normal nd;
+          v = rd.normal(nd);
+        } else {
+          const int sh = sg.shape_base + (sg.shape_mod ? i % sg.shape_mod : 0);
+          v = rd.gamma(a1[sh], a2[sh]);
+        }
+        out[sg.out0 + i] = v;
+        i++;
+      }
+      while (seg < prog.n_segments && i >= prog.seg[seg].count)
+        seg++, i = 0;
+      s_seg = seg, s_i = i, s_pos = rd.pos;
+      if (rd.error)
+        ctl->error = 1, s_done = 1;
+      if (seg >= prog.n_segments) {
+        s_done = 1;
+        ctl->pos[stage_out] = rd.pos;
+      }
     }
     __syncthreads();
-    head = ctl[0], avail = ctl[1];
-    __syncthreads(); // ctl is rewritten by the next draw
   }
+}
 
-  // ---- bulk: `count` fresh normals in a row -----------------------------------------------------
-  // Writes, for the k-th accepted polar attempt, the pair (y, r2) to raw[k]; the transform
-  // z = y * sqrt(-2 log(r2) / r2) runs afterwards over the whole array on all SMs
-  // (k_mt_finish_normals) — log() is the expensive part and has no business in a one-CTA kernel.
-  // Each warp owns a contiguous range of the buffered attempts, its lanes stride over it; one
-  // ballot per 32 attempts gives the compaction offsets, one barrier per round the warp bases.
-  __device__ void bulk_normals(Real *raw, long long count) {
+// ------------------------------------------------------------------------------------------------
+// Bulk: `count` fresh normals in a row = the first `count` accepted polar attempts from the
+// position of stage_in.  Thread t of CTA c owns MT_BULK_PER_THREAD consecutive attempts.
+// ------------------------------------------------------------------------------------------------
+constexpr int MT_BULK_THREADS = 256;
+constexpr int MT_BULK_PER_THREAD = 8;
+constexpr int MT_BULK_TILE = MT_BULK_THREADS * MT_BULK_PER_THREAD;
+
+template <typename Real> struct MtBulkTile {
+  Real y[MT_BULK_PER_THREAD], r2[MT_BULK_PER_THREAD];
+  unsigned accept = 0; // bit u: attempt u of this thread accepted
+  int n = 0;
+
+  __device__ __forceinline__ void evaluate(const uint32_t *__restrict__ ring, unsigned long long mask,
+                                           unsigned long long pos, long long first_attempt, long long n_attempts) {
     constexpr int WPA = MtTraits<Real>::WPA;
-    constexpr int NWARPS = MT_THREADS / 32;
-    constexpr int MAX_ATTEMPTS = MT_BUF_WORDS / WPA;
-    constexpr int KMAX = ((MAX_ATTEMPTS + NWARPS - 1) / NWARPS + 31) / 32;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int round = 0;
-    while (count > 0) {
-      if (count >= MAX_ATTEMPTS)
-        fill(); // every attempt of the buffer will be consumed
-      else
-        ensure(WPA); // tail: one block at a time, so that the state can be handed over exactly
-      int *used_attempts = ctl + 4 + (round++ & 1);
-      const int A = avail / WPA;
-      const int h = head;
-      const int S = (A + NWARPS - 1) / NWARPS;
-      const int wa0 = min(A, wid * S), wa1 = min(A, wa0 + S);
-      unsigned masks[KMAX];
-      Real ys[KMAX], r2s[KMAX];
-      int cnt = 0;
 #pragma unroll
-      for (int k = 0; k < KMAX; k++) {
-        const int a = wa0 + k * 32 + lane;
+    for (int u = 0; u < MT_BULK_PER_THREAD; u++) {
+      const long long a = first_attempt + u;
+      y[u] = 0, r2[u] = 1;
+      if (a < n_attempts) {
+        uint32_t w[WPA];
+        const unsigned long long p = pos + static_cast<unsigned long long>(a) * WPA;
+#pragma unroll
+        for (int k = 0; k < WPA; k++)
+          w[k] = ring[(p + k) & mask];
         Real x;
-        ys[k] = 0, r2s[k] = 0;
-        bool ok = false;
-        if (a < wa1)
-          ok = mt_polar<Real>(buf + h + a * WPA, x, ys[k], r2s[k]);
-        masks[k] = __ballot_sync(FULL_MASK, ok);
-        cnt += __popc(masks[k]);
+        if (mt_polar<Real>(w, x, y[u], r2[u]))
+          accept |= 1u << u, n++;
       }
-      if (lane == 0)
-        warp_tot[wid] = cnt;
-      if (threadIdx.x == 0)
-        *used_attempts = A; // lowered below when the segment ends inside this round
-      __syncthreads();
-      int off = 0, total = 0;
-#pragma unroll
-      for (int k = 0; k < NWARPS; k++) {
-        const int v = warp_tot[k];
-        if (k < wid)
-          off += v;
-        total += v;
-      }
-      const long long want = count < total ? count : total; // normals taken from this round
-      const bool completes = count <= total;                // the segment ends inside this round
-#pragma unroll
-      for (int k = 0; k < KMAX; k++) {
-        const unsigned m = masks[k];
-        if ((m >> lane) & 1u) {
-          const int idx = off + __popc(m & lt_mask);
-          if (idx < want) {
-            raw[2 * static_cast<long long>(idx)] = ys[k];
-            raw[2 * static_cast<long long>(idx) + 1] = r2s[k];
-          }
-          if (completes && idx + 1 == want)
-            *used_attempts = wa0 + k * 32 + lane + 1; // produced the segment's last normal
-        }
-        off += __popc(m);
-      }
-      __syncthreads();
-      const int used = *used_attempts * WPA;
-      head += used, avail -= used;
-      raw += 2 * want, count -= want;
     }
   }
 };
 
-// z[i] = y * sqrt(-2 log(r2) / r2) for the bulk segments (normal_distribution::operator(),
-// bits/random.tcc:1836-1839); raw holds (y, r2) per variate, indexed like z.
 template <typename Real>
-__global__ void __launch_bounds__(256)
-    k_mt_finish_normals(const Real *__restrict__ raw, Real *__restrict__ z, long long begin0,
-                        long long n0, long long begin1, long long n1) {
-  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= n0 + n1)
-    return;
-  i = i < n0 ? begin0 + i : begin1 + (i - n0);
-  const Real y = raw[2 * i], r2 = raw[2 * i + 1];
-  z[i] = y * mt_polar_mult(r2);
+__global__ void __launch_bounds__(MT_BULK_THREADS)
+    k_mt_bulk_count(MtControl *ctl, const uint32_t *__restrict__ ring, unsigned long long mask, int stage_in,
+                    long long n_attempts, int *__restrict__ tile_count) {
+  __shared__ int scratch[32];
+  const unsigned long long pos = ctl->pos[stage_in];
+  if (blockIdx.x == 0 && threadIdx.x == 0 &&
+      pos + static_cast<unsigned long long>(n_attempts) * MtTraits<Real>::WPA > ctl->produced)
+    ctl->error = 1;
+  MtBulkTile<Real> tile;
+  tile.evaluate(ring, mask, pos,
+                static_cast<long long>(blockIdx.x) * MT_BULK_TILE + threadIdx.x * MT_BULK_PER_THREAD, n_attempts);
+  const int total = block_sum(tile.n, scratch);
+  if (threadIdx.x == 0)
+    tile_count[blockIdx.x] = total;
 }
 
-// The variates of one regression sweep in the reference's consumption order
-// (BaseFMTrainer.hpp:135-152; rng.hpp: SweepLayout).
-template <typename Real>
-__global__ void __launch_bounds__(MT_THREADS)
-    k_mt_sweep_variates(MtDeviceState *state, MtProgram prog, Real *__restrict__ out,
-                        Real *__restrict__ raw, int *error) {
-  __shared__ uint32_t s_state[2][MT_N];
-  __shared__ uint32_t s_buf[MT_BUF_WORDS];
-  __shared__ int s_ctl[8];
-  __shared__ int s_warp[32];
-  MtCta<Real> c;
-  c.cur = s_state[0], c.prev = s_state[1], c.buf = s_buf, c.ctl = s_ctl, c.warp_tot = s_warp;
-  for (int i = threadIdx.x; i < MT_N; i += blockDim.x)
-    c.cur[i] = state->x[i];
-  if (threadIdx.x < 8)
-    s_ctl[threadIdx.x] = 0;
+// Exclusive prefix sum of the tile counts (one CTA; a few thousand tiles at most per launch).
+__global__ void __launch_bounds__(1024) k_mt_bulk_scan(int n_tiles, const int *__restrict__ tile_count,
+                                                       long long *__restrict__ tile_offset) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0)
+    carry = 0;
   __syncthreads();
-  c.append_initial(state->p);
-
-  const Real *a1 = static_cast<const Real *>(prog.a1), *a2 = static_cast<const Real *>(prog.a2);
-  const int G = prog.G, K = prog.K;
-  if (prog.g_alpha >= 0)
-    c.scalar(1, a1[G], a2[G], out + prog.g_alpha);
-  if (prog.z_w0 >= 0)
-    c.scalar(0, 0, 0, out + prog.z_w0);
-  for (int g = 0; g < G; g++)
-    c.scalar(1, a1[g], a2[g], out + prog.g_lw + g);
-  for (int g = 0; g < G; g++)
-    c.scalar(0, 0, 0, out + prog.z_mw + g);
-  if (prog.z_w >= 0)
-    c.bulk_normals(raw + 2 * prog.z_w, prog.dim_all);
-  for (int r = 0; r < K; r++)
-    for (int g = 0; g < G; g++)
-      c.scalar(1, a1[g], a2[g], out + prog.g_lV + static_cast<long long>(r) * G + g);
-  for (long long i = 0; i < static_cast<long long>(K) * G; i++)
-    c.scalar(0, 0, 0, out + prog.z_mV + i);
-  c.bulk_normals(raw + 2 * prog.z_V, static_cast<long long>(K) * prog.dim_all);
-
-  // hand the generator over: the unconsumed words are the tail of [prev block][cur block]
-  __syncthreads();
-  const int left = c.avail, last = c.last;
-  const uint32_t *src = left <= last ? c.cur : c.prev;
-  const uint32_t p = left <= last ? MT_N - left : 2 * MT_N - left;
-  for (int i = threadIdx.x; i < MT_N; i += blockDim.x)
-    state->x[i] = src[i];
-  if (threadIdx.x == 0) {
-    state->p = p;
-    if (s_ctl[3] || left > last + MT_N)
-      *error = 1;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const long long v = i < n_tiles ? tile_count[i] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long up = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o)
+        incl += up;
+    }
+    if (lane == 31)
+      warp_tot[wid] = incl;
+    __syncthreads();
+    long long before = carry;
+    for (int w = 0; w < wid; w++)
+      before += warp_tot[w];
+    if (i < n_tiles)
+      tile_offset[i] = before + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023)
+      carry = before + incl;
+    __syncthreads();
   }
+  if (threadIdx.x == 0)
+    tile_offset[n_tiles] = carry;
+}
+
+// z[out0 + k] = y * sqrt(-2 log(r2) / r2) of the k-th accepted attempt, k < count
+// (normal_distribution::operator(), bits/random.tcc:1836-1839); the attempt that yields the last
+// one fixes the stream position of stage_out.
+template <typename Real>
+__global__ void __launch_bounds__(MT_BULK_THREADS)
+    k_mt_bulk_emit(MtControl *ctl, const uint32_t *__restrict__ ring, unsigned long long mask, int stage_in,
+                   int stage_out, long long n_attempts, long long count, const long long *__restrict__ tile_offset,
+                   int n_tiles, Real *__restrict__ out, long long out0) {
+  __shared__ int warp_tot[32];
+  const unsigned long long pos = ctl->pos[stage_in];
+  const long long first = static_cast<long long>(blockIdx.x) * MT_BULK_TILE + threadIdx.x * MT_BULK_PER_THREAD;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && tile_offset[n_tiles] < count)
+    ctl->error = 2;
+  if (tile_offset[blockIdx.x] >= count)
+    return;
+  MtBulkTile<Real> tile;
+  tile.evaluate(ring, mask, pos, first, n_attempts);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = tile.n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o)
+      incl += up;
+  }
+  if (lane == 31)
+    warp_tot[wid] = incl;
+  __syncthreads();
+  long long k = tile_offset[blockIdx.x] + incl - tile.n;
+  for (int w = 0; w < wid; w++)
+    k += warp_tot[w];
+#pragma unroll
+  for (int u = 0; u < MT_BULK_PER_THREAD; u++)
+    if ((tile.accept >> u) & 1u) {
+      if (k < count) {
+        out[out0 + k] = tile.y[u] * mt_polar_mult(tile.r2[u]);
+        if (k == count - 1)
+          ctl->pos[stage_out] = pos + static_cast<unsigned long long>(first + u + 1) * MtTraits<Real>::WPA;
+      }
+      k++;
+    }
 }
 
 } // namespace myfm
