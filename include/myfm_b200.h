@@ -136,7 +136,8 @@ int myfm_trainer_sync(myfm_trainer_t *t);
  * sides); writes the device-side milliseconds. */
 int myfm_trainer_timed_steps(myfm_trainer_t *t, int32_t n_sweeps, double *ms);
 
-/* Current state (synchronises).  w: [dim_all]; V: [dim_all x rank] row-major. */
+/* Current state (synchronises).  w: [dim_all]; V: [dim_all x rank] row-major.  In get_fm any of
+ * w0 / w / V may be NULL (that part is not copied). */
 int myfm_trainer_dims(const myfm_trainer_t *t, int64_t *n_train, int64_t *dim_all, int32_t *rank,
                       int32_t *n_groups);
 int myfm_trainer_get_fm(myfm_trainer_t *t, double *w0, double *w, double *V);

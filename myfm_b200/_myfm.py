@@ -370,7 +370,8 @@ class _LiveFM(FM):
             self._cache = self._trainer.get_fm()
         return self._cache
 
-    w0 = property(lambda self: self._fetch()[0])
+    # the bias alone does not pull the whole sample over the bus
+    w0 = property(lambda self: self._trainer.get_w0() if self._cache is None else self._cache[0])
     w = property(lambda self: self._fetch()[1])
     V = property(lambda self: self._fetch()[2])
     cutpoints = property(lambda self: self._fetch()[3])
@@ -590,6 +591,11 @@ class _TrainerHandle:
                 _lib.check(_lib.lib().myfm_trainer_get_cutpoints(self._h, C.c_int32(g), _lib.vptr(a)))
                 cps.append(a)
         return w0.value, w, V, cps
+
+    def get_w0(self) -> float:
+        w0 = C.c_double()
+        _lib.check(_lib.lib().myfm_trainer_get_fm(self._h, C.byref(w0), None, None))
+        return w0.value
 
     def get_hyper(self) -> FMHyperParameters:
         G, K = self.n_groups, self.rank

@@ -161,6 +161,8 @@ template <typename Real> struct Dataset : DatasetBase {
   }
 
   void count(int n = 1) { (launch_counter ? *launch_counter : own_counter) += n; }
+  int row_len = 0;   // > 0: every row of X holds exactly this many entries
+  bool unit = false; // every stored value of X is 1
 
   // Shape checks of util.hpp:147-165 / definitions.hpp:38-41, then upload.
   // `perm` (trainer only): device row i holds the caller's row perm[i]; Xh is already permuted.
@@ -171,6 +173,11 @@ template <typename Real> struct Dataset : DatasetBase {
     dim_main = Xh.n_minor;
     dim_all = dim_main;
     X.upload(Xh, s);
+    row_len = Xh.n_major ? Xh.ptr[1] - Xh.ptr[0] : 0;
+    for (int64_t i = 0; i < Xh.n_major && row_len > 0; i++)
+      if (Xh.ptr[i + 1] - Xh.ptr[i] != row_len)
+        row_len = 0;
+    unit = std::all_of(Xh.val.begin(), Xh.val.end(), [](Real v) { return v == Real(1); });
     if (n_rel > MAX_REL)
       throw std::invalid_argument("too many relation blocks (at most 8 are supported).");
     rels.resize(n_rel);
@@ -230,6 +237,46 @@ template <typename Real> struct Dataset : DatasetBase {
       return;
     const int lpr = pow2_ceil_clamped(K / 4.0, 1, 32);
     const int n = static_cast<int>(n_rows);
+    if (K >= 16 && K <= 64 && pack.n == 0 && row_len >= 1 && row_len <= 4 && (out_stride == 1 || out_stride == 2)) {
+      // fixed-length rows, wide factors: warp per tile of 32 rows (k_predict_tile)
+      int sms = 0, dev = 0;
+      MYFM_CUDA(cudaGetDevice(&dev));
+      MYFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const int grid = std::min(ceil_div(static_cast<int64_t>(ceil_div(n, 32)) * 32, 256), sms * 8);
+#define MYFM_TILE4(LL, U, KPL)                                                                     \
+  if (out_stride == 2)                                                                             \
+    k_predict_tile<Real, LL, U, KPL, true><<<grid, 256, 0, stream>>>(n, X.idx.p, X.val.p, w_dev, Vt_dev, K, w0_dev, y,  \
+                                                                     out, out_stride);             \
+  else                                                                                             \
+    k_predict_tile<Real, LL, U, KPL, false><<<grid, 256, 0, stream>>>(n, X.idx.p, X.val.p, w_dev, Vt_dev, K, w0_dev, y, \
+                                                                      out, out_stride);
+#define MYFM_TILE3(LL, U)                                                                          \
+  if (K <= 32) {                                                                                   \
+    MYFM_TILE4(LL, U, 1)                                                                           \
+  } else {                                                                                         \
+    MYFM_TILE4(LL, U, 2)                                                                           \
+  }
+#define MYFM_TILE2(LL)                                                                             \
+  case LL:                                                                                         \
+    if (unit) {                                                                                    \
+      MYFM_TILE3(LL, true)                                                                         \
+    } else {                                                                                       \
+      MYFM_TILE3(LL, false)                                                                        \
+    }                                                                                              \
+    break;
+      switch (row_len) {
+        MYFM_TILE2(1)
+        MYFM_TILE2(2)
+        MYFM_TILE2(3)
+        MYFM_TILE2(4)
+      }
+#undef MYFM_TILE2
+#undef MYFM_TILE3
+#undef MYFM_TILE4
+      count();
+      MYFM_CUDA(cudaGetLastError());
+      return;
+    }
     if (K >= 16 && K <= 64 && X.avg_len() <= 16) { // short rows, wide factors: warp per row tile
       const int warps = ceil_div(n, PREDICT_ROWS_PER_WARP);
       const int grid = ceil_div(static_cast<int64_t>(warps) * 32, 256);
@@ -592,6 +639,7 @@ template <typename Real> struct Trainer : TrainerBase {
   ~Trainer() override {
     if (stream)
       cudaStreamSynchronize(stream);
+    reset_graphs();
     if (rng_stream)
       cudaStreamSynchronize(rng_stream);
     if (comm)
@@ -647,6 +695,13 @@ template <typename Real> struct Trainer : TrainerBase {
     hyper.upload(hh, stream);
     layout = SweepLayout::make(cfg.task_type == MYFM_TASK_REGRESSION, cfg.fit_w0, cfg.fit_linear, G,
                                K, D_all);
+    reset_graphs();
+    {
+      const char *no_graph = std::getenv("MYFM_NO_GRAPH");
+      use_graphs = !(no_graph && no_graph[0] == '1');
+    }
+    if (field_path)
+      f_sched.alloc(static_cast<size_t>(K) + 2);
     setup_rng();
     const bool ordered = cfg.task_type == MYFM_TASK_ORDERED;
     data.predict(w.p, Vt.p, K, hv().w0, ordered ? nullptr : y.p, e_ptr(), 2);
@@ -1369,30 +1424,22 @@ template <typename Real> struct Trainer : TrainerBase {
     return 1;
   }
 
-  // update_all (BaseFMTrainer.hpp:135-152)
-  void sweep() {
-    const int slot = static_cast<int>(sweep_index & 1);
-    const Real *z = nullptr;
-    if (device_rng) {
-      while (gen_index <= sweep_index + 1) // this sweep's variates, and the next one's ahead of time
-        launch_variates(gen_index++);
-      MYFM_CUDA(cudaStreamWaitEvent(stream, z_ready[slot], 0));
-      z = z_slot[slot].p;
-    } else {
-      if (sweep_index >= 2)
-        MYFM_CUDA(cudaEventSynchronize(z_copied[slot]));
-      draw_sweep_variates(z_pinned[slot].p);
-      MYFM_CUDA(cudaMemcpyAsync(z_dev.p, z_pinned[slot].p, layout.total * sizeof(Real),
-                                cudaMemcpyHostToDevice, stream));
-      MYFM_CUDA(cudaEventRecord(z_copied[slot], stream));
-      z = z_dev.p;
+  // The device work of one update_all after the variates are in place: kernel launches and memsets
+  // on `stream` only (capturable).
+  cudaGraphExec_t sweep_graph[2] = {nullptr, nullptr};
+  int64_t sweep_graph_launches[2] = {0, 0};
+  bool use_graphs = true;
+  void reset_graphs() {
+    for (auto &g : sweep_graph) {
+      if (g)
+        cudaGraphExecDestroy(g);
+      g = nullptr;
     }
-    z_last = z;
+  }
+  void sweep_body(const Real *z) {
     HyperView<Real> h = hv();
     const SweepLayout &L = layout;
     if (field_path) { // work counters of this sweep's streaming passes; nothing is pending after update_e
-      if (f_sched.n < static_cast<size_t>(K) + 2)
-        f_sched.alloc(static_cast<size_t>(K) + 2);
       f_sched.zero(stream);
       f_launch = 0, f_pending_valid = false;
     }
@@ -1434,6 +1481,56 @@ template <typename Real> struct Trainer : TrainerBase {
     { // update_e
       TimedSpan span(timer, stream, 2);
       data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e_ptr(), 2);
+    }
+  }
+
+  // update_all (BaseFMTrainer.hpp:135-152)
+  void sweep() {
+    const int slot = static_cast<int>(sweep_index & 1);
+    const Real *z = nullptr;
+    if (device_rng) {
+      while (gen_index <= sweep_index + 1) // this sweep's variates, and the next one's ahead of time
+        launch_variates(gen_index++);
+      MYFM_CUDA(cudaStreamWaitEvent(stream, z_ready[slot], 0));
+      z = z_slot[slot].p;
+    } else {
+      if (sweep_index >= 2)
+        MYFM_CUDA(cudaEventSynchronize(z_copied[slot]));
+      draw_sweep_variates(z_pinned[slot].p);
+      MYFM_CUDA(cudaMemcpyAsync(z_dev.p, z_pinned[slot].p, layout.total * sizeof(Real),
+                                cudaMemcpyHostToDevice, stream));
+      MYFM_CUDA(cudaEventRecord(z_copied[slot], stream));
+      z = z_dev.p;
+    }
+    z_last = z;
+    // Regression with the device RNG never needs the host inside a sweep: the launch sequence of a
+    // slot is captured once into a CUDA graph and replayed (the first sweep of each slot runs
+    // directly: first-use allocations and function attributes are not capturable).
+    const bool graphable = device_rng && world == 1 && cfg.task_type == MYFM_TASK_REGRESSION && !timer.enabled &&
+                           use_graphs && sweep_index >= 2;
+    if (graphable) {
+      if (!sweep_graph[slot]) {
+        const int64_t before = launches;
+        cudaGraph_t g = nullptr;
+        MYFM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          sweep_body(z);
+        } catch (...) {
+          cudaStreamEndCapture(stream, &g);
+          if (g)
+            cudaGraphDestroy(g);
+          throw;
+        }
+        MYFM_CUDA(cudaStreamEndCapture(stream, &g));
+        MYFM_CUDA(cudaGraphInstantiate(&sweep_graph[slot], g, 0));
+        MYFM_CUDA(cudaGraphDestroy(g));
+        sweep_graph_launches[slot] = launches - before;
+        launches = before;
+      }
+      MYFM_CUDA(cudaGraphLaunch(sweep_graph[slot], stream));
+      launches += sweep_graph_launches[slot];
+    } else {
+      sweep_body(z);
     }
     if (cfg.task_type == MYFM_TASK_CLASSIFICATION)
       classification_latent();
@@ -1501,16 +1598,20 @@ template <typename Real> struct Trainer : TrainerBase {
     return h;
   }
 
-  void get_fm(double *w0_out, double *w_out, double *V_out) override {
+  void get_fm(double *w0_out, double *w_out, double *V_out) override { // any of the three may be NULL
     require_fm();
-    auto hh = fetch(hyper.p, 2);
-    auto wh = fetch(w.p, D_all);
-    auto Vh = fetch(Vt.p, static_cast<size_t>(D_all) * K);
-    *w0_out = hh[1];
-    for (int64_t i = 0; i < D_all; i++)
-      w_out[i] = wh[i];
-    for (size_t i = 0; i < Vh.size(); i++)
-      V_out[i] = Vh[i];
+    if (w0_out)
+      *w0_out = fetch(hyper.p, 2)[1];
+    if (w_out) {
+      auto wh = fetch(w.p, D_all);
+      for (int64_t i = 0; i < D_all; i++)
+        w_out[i] = wh[i];
+    }
+    if (V_out) {
+      auto Vh = fetch(Vt.p, static_cast<size_t>(D_all) * K);
+      for (size_t i = 0; i < Vh.size(); i++)
+        V_out[i] = Vh[i];
+    }
   }
   void get_cutpoints(int g, double *out) override {
     if (g < 0 || g >= static_cast<int>(cut_groups.size()))

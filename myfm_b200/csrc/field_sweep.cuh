@@ -216,7 +216,7 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
   Real sq = 0, lin = 0;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
-    b.finish(a, s_told, s_tnew, s_tnext, s, i0 + NT * s, theta_old, e[s], q[s], x0[s]);
+    b.finish(a, s_told, s_tnew, s_tnext, s, ok[s] ? i0 + NT * s : it.z - 1, theta_old, e[s], q[s], x0[s]);
     if (ok[s])
       field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
   }

@@ -227,6 +227,90 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Forward pass for tables whose rows all hold exactly L entries (one-hot / categorical fields)
+// and 16 <= K <= 64.  One warp per tile of 32 consecutive rows: the lanes own factors (KPL per
+// lane), walk the tile's rows with the entries broadcast by shuffle and read every V row as one
+// coalesced line; the 32 per-row sums are then reduced across the lanes by a 31-shuffle transposed
+// butterfly (one shuffle per row instead of five) and lane l finishes row l.
+// PAIR: out is the trainer's interleaved {e, q} array; both halves are written (q = 0) so that
+// whole sectors are stored.
+template <typename Real, int L, bool UNIT, int KPL, bool PAIR>
+__global__ void __launch_bounds__(256)
+    k_predict_tile(int n_rows, const int *__restrict__ idx, const Real *__restrict__ val,
+                   const Real *__restrict__ w, const Real *__restrict__ Vt, int K,
+                   const Real *__restrict__ w0_ptr, const Real *__restrict__ y, Real *__restrict__ out,
+                   int out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (n_rows + 31) >> 5;
+  const Real w0 = *w0_ptr, half = static_cast<Real>(0.5);
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += (gridDim.x * blockDim.x) >> 5) {
+    const int row = tile * 32 + lane;
+    const bool valid = row < n_rows;
+    const int64_t p0 = static_cast<int64_t>(valid ? row : n_rows - 1) * L;
+    int j[L];
+    Real x[L];
+    Real lin = 0;
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+      j[k] = __ldcs(idx + p0 + k);
+      x[k] = UNIT ? Real(1) : __ldcs(val + p0 + k);
+      lin += x[k] * w[j[k]];
+    }
+    Real part[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; rr++) {
+      Real q[KPL], s[KPL];
+#pragma unroll
+      for (int u = 0; u < KPL; u++)
+        q[u] = 0, s[u] = 0;
+#pragma unroll
+      for (int k = 0; k < L; k++) {
+        const int jk = __shfl_sync(FULL_MASK, j[k], rr);
+        const Real xk = UNIT ? Real(1) : __shfl_sync(FULL_MASK, x[k], rr);
+        const Real *vrow = Vt + static_cast<int64_t>(jk) * K;
+#pragma unroll
+        for (int u = 0; u < KPL; u++)
+          if (lane + 32 * u < K) {
+            const Real v = vrow[lane + 32 * u];
+            q[u] += xk * v;
+            s[u] += (xk * xk) * (v * v);
+          }
+      }
+      Real tot = 0;
+#pragma unroll
+      for (int u = 0; u < KPL; u++)
+        if (lane + 32 * u < K) {
+          tot += (q[u] * q[u]) * half;
+          tot -= s[u] * half;
+        }
+      part[rr] = tot;
+    }
+    // transposed butterfly: afterwards part[0] of lane l is the sum over the lanes of part[l]
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; i++) {
+        const Real send = upper ? part[i] : part[i + o];
+        const Real keep = upper ? part[i + o] : part[i];
+        part[i] = keep + __shfl_xor_sync(FULL_MASK, send, o);
+      }
+    }
+    if (valid) {
+      Real t = (w0 + lin) + part[0];
+      if (y)
+        t = t - y[row];
+      if (PAIR) {
+        Pair<Real> v;
+        v.x = t, v.y = 0;
+        __stcg(reinterpret_cast<Pair<Real> *>(out) + row, v);
+      } else {
+        out[static_cast<size_t>(row) * out_stride] = t;
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Scalars of one sweep live in a small device array so that no step needs the host.
 // ----------------------------------------------------------------------------------------------

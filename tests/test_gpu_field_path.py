@@ -105,3 +105,22 @@ def test_field_path_equals_general_path(engine, oracle):
             np.testing.assert_allclose(xa, xb, rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(a.get_e(), b.get_e(), rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(a.get_q(), b.get_q(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("rank,unit,fields", [(20, True, [60, 25]), (40, False, [30, 20, 10]), (33, True, [40, 9, 5, 4])])
+def test_wide_rank_forward_pass(engine, oracle, rank, unit, fields):
+    """16 <= rank <= 64 with fixed-length rows: the tile forward pass (k_predict_tile, one or two
+    factors per lane) refreshes e; also through the prediction-dataset entry point."""
+    X, y, gs = fields_like(3000, fields, 3, seed=11, unit=unit)
+    t, chain = make_pair(engine, oracle, X, y, rank, "f64", group_shapes=gs)
+    run_chain_parity(t, chain, "f64", 3)
+    from myfm_b200._myfm import FM
+
+    w0, w, V, _ = t.get_fm()
+    with engine.engine_options(dtype="f64"):
+        score = FM(w0, w, V).predict_score(X[:1000], [])
+    Xd = X[:1000]
+    X2 = Xd.copy()
+    X2.data = X2.data ** 2
+    ref = w0 + Xd.dot(w) + 0.5 * ((Xd.dot(V) ** 2).sum(1) - X2.dot((V ** 2).sum(1)))
+    np.testing.assert_allclose(score, ref, rtol=1e-9, atol=1e-9)
