@@ -167,7 +167,8 @@ int myfm_trainer_sweep_path(const myfm_trainer_t *t, int32_t *path);
 /* number of kernels this trainer has launched so far (bench.py's gpu_launches) */
 int myfm_trainer_launch_count(const myfm_trainer_t *t, int64_t *count);
 /* device milliseconds spent in the dominant kernel family since the last call (CUDA events on
- * the trainer's stream); family: 0 = column sweeps, 1 = q_init, 2 = e_refresh */
+ * the trainer's stream); family: 0 = column sweeps, 1 = q_init, 2 = e_refresh, and inside family 0 on
+ * the field path: 3 = streaming level (k_field_stream), 4 = gather-only level (k_field_stats) */
 int myfm_trainer_kernel_ms(myfm_trainer_t *t, int32_t family, double *ms, int64_t *launches);
 /* turn the per-family CUDA-event timing on or off (off by default; adds two event records per
  * launch group when on) */

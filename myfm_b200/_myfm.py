@@ -390,8 +390,9 @@ class _LiveFM(FM):
         return self.freeze().oprobit_predict_proba(X, relations, cutpoint_index)
 
     def freeze(self) -> FM:
-        w0, w, V, cps = self._fetch()
-        return FM(w0, w.copy(), V.copy(), [c.copy() for c in cps])
+        w0, w, V, cps = self._fetch()  # freshly downloaded arrays owned by this transient view
+        self._cache = None
+        return FM(w0, w, V, cps)
 
     def __getstate__(self):
         return self.freeze().__getstate__()

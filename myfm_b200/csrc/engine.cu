@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -103,8 +104,9 @@ struct KernelTimer {
     size_t a, b;
   };
   std::vector<Span> spans;
-  double ms[3] = {0, 0, 0};
-  int64_t launches[3] = {0, 0, 0};
+  static constexpr int FAMILIES = 5; // 0 column sweeps, 1 q_init, 2 e_refresh, 3 streaming level, 4 gather level
+  double ms[FAMILIES] = {0, 0, 0, 0, 0};
+  int64_t launches[FAMILIES] = {0, 0, 0, 0, 0};
   ~KernelTimer() {
     for (auto e : pool)
       cudaEventDestroy(e);
@@ -395,7 +397,7 @@ template <typename Real> struct Trainer : TrainerBase {
   bool f_pending_valid = false; // the last level's draw of the previous vector awaits the next pass
   SweepLevel f_level0, f_levelL;
   DevBuf<SweepItem> f_items0, f_itemsL;
-  DevBuf<int> f_seg_countL, f_tail_idx, f_sched;
+  DevBuf<int> f_seg_countL, f_tail_idx, f_sched, f_chunk_done;
   DevBuf<Real> f_tail_val, f_own_val, f_pend_told, f_pend_tnew, f_partial;
 
   int64_t N = 0, D = 0, D_all = 0;
@@ -465,7 +467,19 @@ template <typename Real> struct Trainer : TrainerBase {
         throw std::runtime_error("row-sharded training supports regression only: the reference's latent draws "
                                  "for classification / ordered probit consume the mt19937 stream row by row.");
     }
+    const char *trace_env = std::getenv("MYFM_TRACE_SETUP");
+    const bool trace = trace_env && trace_env[0] == '1';
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+      if (!trace)
+        return;
+      auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[myfm_b200 setup] %-28s %8.1f ms\n", what,
+                   std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     HostCs<Real> Xh = host_from_api<Real>(X_api, "X");
+    tick("copy + validate CSR");
     if (Xh.n_major != n_y) { // BaseFMTrainer.hpp:69-76
       std::ostringstream ss;
       ss << "Shape mismatch: X has size " << Xh.n_major << " and y has size " << n_y;
@@ -474,11 +488,13 @@ template <typename Real> struct Trainer : TrainerBase {
     if (has_duplicate_entries(Xh))
       throw std::invalid_argument(
           "X lists the same (row, column) twice; sum duplicates first (X.sum_duplicates()).");
+    tick("duplicate check");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device)
       throw CudaError("no usable CUDA device: the myfm_b200 engine has no CPU fallback.");
     MYFM_CUDA(cudaSetDevice(device));
     MYFM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    tick("CUDA context + streams");
     MYFM_CUDA(cudaStreamCreateWithFlags(&rng_stream, cudaStreamNonBlocking));
     for (auto &ev : z_copied)
       MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -490,6 +506,7 @@ template <typename Real> struct Trainer : TrainerBase {
     // dependency levels, device row order, sweep work items (host_data.hpp)
     {
       HostCs<Real> Xth0 = host_transpose(Xh);
+      tick("transpose");
       int n_levels = 0, primary = -1;
       std::vector<int> level;
       if (o.column_level) { // agreed between the ranks (myfm_level_relax + max all-reduce)
@@ -509,19 +526,25 @@ template <typename Real> struct Trainer : TrainerBase {
           throw std::invalid_argument("row-sharded training needs column_level agreed between the ranks.");
         level = compute_levels(Xth0, &n_levels);
       }
+      tick("dependency levels");
       perm = primary_row_order(Xth0, level, n_levels, &primary);
       Xh = permute_rows(Xh, perm);
+      tick("row order + permute");
       main_unit = std::all_of(Xh.val.begin(), Xh.val.end(), [](Real v) { return v == Real(1); });
       main_row_len = Xh.n_major ? Xh.ptr[1] - Xh.ptr[0] : 0;
       for (int64_t i = 0; i < Xh.n_major && main_row_len > 0; i++)
         if (Xh.ptr[i + 1] - Xh.ptr[i] != main_row_len)
           main_row_len = 0;
+      tick("unit / row-length scan");
       HostCs<Real> Xth = host_transpose(Xh);
+      tick("transpose (device order)");
       plan = make_sweep_plan(Xth, level, n_levels, SWEEP_WARP_MAX, SWEEP_CHUNK);
       plan.primary_level = primary;
+      tick("sweep plan");
       Xt.upload(Xth, stream);
       setup_field_path(Xh, Xth, level, n_levels, n_rel);
       MYFM_CUDA(cudaStreamSynchronize(stream));
+      tick("CSC upload + field path");
     }
     perm_dev.upload(perm, stream);
     items.upload(plan.items, stream);
@@ -536,6 +559,7 @@ template <typename Real> struct Trainer : TrainerBase {
 
     data.launch_counter = &launches;
     data.build(Xh, n_rel, relations, stream, &perm);
+    tick("CSR upload");
     N = data.n_rows, D = data.dim_main, D_all = data.dim_all;
     if (static_cast<int64_t>(cfg.group_index.size()) != D_all)
       throw std::invalid_argument("group_index must have one entry per feature.");
@@ -1027,6 +1051,8 @@ template <typename Real> struct Trainer : TrainerBase {
     f_itemsL.upload(pL.items, stream);
     f_seg_countL.upload(pL.seg_count, stream);
     f_partial.alloc(2 * static_cast<size_t>(std::max(1, f_levelL.c0 - f_levelL.s0)));
+    f_chunk_done.alloc(std::max(1, f_levelL.c0 - f_levelL.s0));
+    f_chunk_done.zero(stream);
     std::vector<int> tail(static_cast<size_t>(f_tail) * n);
     for (int64_t i = 0; i < n; i++)
       for (int k = 1; k < L; k++)
@@ -1077,6 +1103,7 @@ template <typename Real> struct Trainer : TrainerBase {
     TimedSpan span(timer, stream, 0);
     const int pend = !f_pending_valid ? PEND_NONE : (IS_V && f_pending_is_v ? PEND_V : PEND_W);
     {
+      TimedSpan span_stream(timer, stream, 3);
       FieldStreamArgs<Real> a;
       a.item = reinterpret_cast<const int4 *>(f_items0.p + f_level0.s0);
       a.nCC = f_nCC, a.nCR = f_nCR, a.nG = f_nG, a.nW = f_nW;
@@ -1110,6 +1137,7 @@ template <typename Real> struct Trainer : TrainerBase {
     if (f_tail > 1)
       sweep_main<IS_V>(theta, theta_t, t_stride, z, lambda, mu, 1, static_cast<size_t>(f_tail));
     {
+      TimedSpan span_stats(timer, stream, 4);
       FieldStatsArgs<Real> a;
       a.idx = Xt.idx.p, a.val = Xt.val.p;
       a.item = reinterpret_cast<const int4 *>(f_itemsL.p + f_levelL.s0);
@@ -1118,7 +1146,7 @@ template <typename Real> struct Trainer : TrainerBase {
       a.eq = eq();
       a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
-      a.partial = f_partial.p, a.last_base = f_last_base;
+      a.partial = f_partial.p, a.chunk_done = f_chunk_done.p, a.last_base = f_last_base;
       a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
       const int grid = a.nS + a.nC + ceil_div(a.nW, STATS_THREADS / 32);
       if (grid) {
@@ -1127,10 +1155,6 @@ template <typename Real> struct Trainer : TrainerBase {
         else
           k_field_stats<Real, IS_V, false><<<grid, STATS_THREADS, 0, stream>>>(a);
         launched();
-        if (a.nS) {
-          k_field_finish_long<Real, IS_V><<<ceil_div(a.nS, 128), 128, 0, stream>>>(a);
-          launched();
-        }
       }
     }
     f_pending_valid = true, f_pending_is_v = IS_V;
@@ -1504,10 +1528,10 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     z_last = z;
     // Regression with the device RNG never needs the host inside a sweep: the launch sequence of a
-    // slot is captured once into a CUDA graph and replayed (the first sweep of each slot runs
-    // directly: first-use allocations and function attributes are not capturable).
+    // slot is captured once into a CUDA graph and replayed (the very first sweep runs directly:
+    // first-use allocations and function attributes are not capturable).
     const bool graphable = device_rng && world == 1 && cfg.task_type == MYFM_TASK_REGRESSION && !timer.enabled &&
-                           use_graphs && sweep_index >= 2;
+                           use_graphs && sweep_index >= 1;
     if (graphable) {
       if (!sweep_graph[slot]) {
         const int64_t before = launches;
@@ -1602,17 +1626,23 @@ template <typename Real> struct Trainer : TrainerBase {
     require_fm();
     if (w0_out)
       *w0_out = fetch(hyper.p, 2)[1];
-    if (w_out) {
-      auto wh = fetch(w.p, D_all);
-      for (int64_t i = 0; i < D_all; i++)
-        w_out[i] = wh[i];
-    }
-    if (V_out) {
-      auto Vh = fetch(Vt.p, static_cast<size_t>(D_all) * K);
-      for (size_t i = 0; i < Vh.size(); i++)
-        V_out[i] = Vh[i];
-    }
+    // widened on the device, then one copy straight into the caller's buffer
+    auto fetch_double = [&](const Real *dev, size_t n, double *out) {
+      if (!n)
+        return;
+      if (wide_tmp.n < n)
+        wide_tmp.alloc(n);
+      k_to_double<Real><<<ceil_div(n, 256), 256, 0, stream>>>(static_cast<int64_t>(n), dev, wide_tmp.p);
+      launched();
+      MYFM_CUDA(cudaMemcpyAsync(out, wide_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+    };
+    if (w_out)
+      fetch_double(w.p, D_all, w_out);
+    if (V_out)
+      fetch_double(Vt.p, static_cast<size_t>(D_all) * K, V_out);
   }
+  DevBuf<double> wide_tmp;
   void get_cutpoints(int g, double *out) override {
     if (g < 0 || g >= static_cast<int>(cut_groups.size()))
       throw std::runtime_error("No cutpoint available for this FM.");
@@ -1704,8 +1734,8 @@ template <typename Real> struct Trainer : TrainerBase {
   int sweep_path() const override { return field_path ? 1 : 0; }
   void kernel_ms(int family, double *ms, int64_t *n) override {
     sync();
-    if (family < 0 || family > 2)
-      throw std::invalid_argument("kernel family must be 0, 1 or 2.");
+    if (family < 0 || family >= KernelTimer::FAMILIES)
+      throw std::invalid_argument("kernel family must be 0 .. 4.");
     *ms = timer.ms[family], *n = timer.launches[family];
     timer.ms[family] = 0, timer.launches[family] = 0;
   }

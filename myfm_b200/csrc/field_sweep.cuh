@@ -28,13 +28,15 @@ namespace myfm {
 
 constexpr int FIELD_THREADS = 1024; // streaming pass: one persistent CTA per SM
 // rows per lane kept in registers between the reduction and the update: 8 (f32), 4 (f64)
-constexpr int FIELD_BATCH = 4;       // level-0 columns a warp takes per scheduling step
+constexpr int FIELD_BATCH = 8;       // level-0 columns a warp takes per scheduling step (at most 32)
 constexpr int FIELD_CTA_MAX = 32768;  // longest level-0 column (one CTA); longer: general path
 constexpr int STATS_THREADS = 256;
-constexpr int STATS_WARP_MAX = 256;   // last level: warp per column up to here,
+constexpr int STATS_WARP_MAX = 2048;  // last level: warp per column up to here (no barrier on the path),
 constexpr int STATS_CHUNK = 8192;     // one CTA per column up to here, chunks of this size beyond
 
 enum { PEND_NONE = 0, PEND_W = 1, PEND_V = 2 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename Real> struct FieldStreamArgs {
   const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
@@ -339,7 +341,10 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
 
   // One warp per column.  The first batch of FIELD_BATCH columns is static, the following ones are
   // handed out through a counter (one atomic per batch: same-address atomics retire at about one
-  // per two cycles chip-wide, one per column would bound the kernel).
+  // per two cycles chip-wide, one per column would bound the kernel).  Lane b of the warp owns the
+  // scalars of the batch's b-th column (item, theta, z, group hypers: one chain of dependent loads
+  // per BATCH, not per column), and the rows of the whole batch are pulled into L2 up front, so a
+  // column's own loads find their lines on chip.
   const int total_warps = gridDim.x * FIELD_WARPS;
   const int4 *items_w = a.item + a.nCC + a.nCR + a.nG;
   int kb = (blockIdx.x + gridDim.x * warp) * FIELD_BATCH; // longest columns spread over the SMs
@@ -347,20 +352,37 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     int kb_next = 0;
     if (lane == 0)
       kb_next = total_warps * FIELD_BATCH + atomicAdd(a.sched, FIELD_BATCH);
-    const int k_end = min(kb + FIELD_BATCH, a.nW);
-    int4 it_next = __ldg(items_w + kb);
-    for (int k = kb; k < k_end; k++) {
-      const int4 it = it_next;
-      if (k + 1 < k_end)
-        it_next = __ldg(items_w + k + 1);
-      const int j = it.x;
-      const Real theta_old = a.theta[j];
-      const int g = a.group[j];
-      const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+    const int n_batch = min(FIELD_BATCH, a.nW - kb);
+    int4 my_it = make_int4(0, 0, 0, 0);
+    Real my_theta = 0, my_lam = 0, my_mu = 0, my_z = 0;
+    if (lane < n_batch) {
+      my_it = __ldg(items_w + kb + lane);
+      my_theta = a.theta[my_it.x];
+      my_z = a.z[my_it.x];
+      const int g = a.group[my_it.x];
+      my_lam = a.lambda[g], my_mu = a.mu[g];
+    }
+    for (int bi = 0; bi < n_batch; bi++) {
+      const int lo = __shfl_sync(FULL_MASK, my_it.y, bi), n = __shfl_sync(FULL_MASK, my_it.z, bi) - lo;
+      const char *p_eq = reinterpret_cast<const char *>(a.eq + lo);
+      for (int off = lane * 128; off < n * static_cast<int>(sizeof(Pair<Real>)); off += 32 * 128)
+        prefetch_l2(p_eq + off);
+      if (IS_V || PEND != PEND_NONE) {
+        const char *p_tail = reinterpret_cast<const char *>(a.tail_last + lo);
+        for (int off = lane * 128; off < n * 4; off += 32 * 128)
+          prefetch_l2(p_tail + off);
+      }
+    }
+    for (int bi = 0; bi < n_batch; bi++) {
+      int4 it;
+      it.x = __shfl_sync(FULL_MASK, my_it.x, bi), it.y = __shfl_sync(FULL_MASK, my_it.y, bi);
+      it.z = __shfl_sync(FULL_MASK, my_it.z, bi), it.w = 0;
+      const Real theta_old = __shfl_sync(FULL_MASK, my_theta, bi), lam = __shfl_sync(FULL_MASK, my_lam, bi);
+      const Real mu = __shfl_sync(FULL_MASK, my_mu, bi), z = __shfl_sync(FULL_MASK, my_z, bi);
       const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, 1>(
           a, s_told, s_tnew, s_tnext, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane);
       if (lane == 0)
-        field_store_theta(a, j, theta_new);
+        field_store_theta(a, it.x, theta_new);
     }
     kb = __shfl_sync(FULL_MASK, kb_next, 0);
   }
@@ -381,7 +403,8 @@ template <typename Real> struct FieldStatsArgs {
   const Real *z;
   const int *group;
   const Real *alpha, *lambda, *mu;
-  Real *partial; // [2 nS]
+  Real *partial;   // [2 nS] chunk statistics of the long columns
+  int *chunk_done; // [nS] chunks finished, per long column (at its first chunk), zero between launches
   int last_base;
   Real *pend_told, *pend_tnew;
 };
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
   const Real theta_old = a.theta[j];
   const int t = cta_item ? threadIdx.x : lane, nt = cta_item ? STATS_THREADS : 32;
   Real sq = 0, lin = 0;
-  constexpr int U = 4; // gathers in flight per thread
+  constexpr int U = 8; // gathers in flight per thread
   for (int p0 = it.y + t; p0 < it.z; p0 += U * nt) {
     int i[U];
     Real x[U];
@@ -438,7 +461,19 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
     lin = block_sum(lin, scratch);
     if (threadIdx.x == 0) {
       if (b < a.nS) {
-        a.partial[2 * b] = sq, a.partial[2 * b + 1] = lin;
+        // chunk of a long column: the chunk that finishes last adds the chunk statistics in chunk
+        // order (deterministic) and draws; it leaves the counter at zero for the next launch
+        __stcg(a.partial + 2 * b, sq), __stcg(a.partial + 2 * b + 1, lin);
+        __threadfence();
+        const int n_chunks = a.seg_count[b];
+        if (atomicAdd(a.chunk_done + it.w, 1) == n_chunks - 1) {
+          __threadfence();
+          Real s = 0, l = 0;
+          for (int i = it.w; i < it.w + n_chunks; i++)
+            s += __ldcg(a.partial + 2 * i), l += __ldcg(a.partial + 2 * i + 1);
+          a.chunk_done[it.w] = 0;
+          field_publish<Real, IS_V>(a, j, s, l, theta_old, alpha);
+        }
       } else {
         field_publish<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
       }
@@ -449,23 +484,6 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
     if (lane == 0)
       field_publish<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
   }
-}
-
-// Long columns: chunk statistics summed in chunk order, then the draw.  One thread per chunk item;
-// only a column's first chunk acts.
-template <typename Real, bool IS_V> __global__ void k_field_finish_long(FieldStatsArgs<Real> a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.nS)
-    return;
-  const int4 it = __ldg(a.item + b);
-  if (it.w != b)
-    return;
-  Real sq = 0, lin = 0;
-  for (int i = b; i < b + a.seg_count[b]; i++) {
-    sq += a.partial[2 * i];
-    lin += a.partial[2 * i + 1];
-  }
-  field_publish<Real, IS_V>(a, it.x, sq, lin, a.theta[it.x], *a.alpha);
 }
 
 } // namespace myfm

@@ -1041,6 +1041,14 @@ __global__ void __launch_bounds__(256)
   out[static_cast<size_t>(i) * (n_cpt + 1) + n_cpt] += 1 - prev;
 }
 
+// widening copy for the getters (the boundary speaks float64)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_to_double(int64_t n, const Real *__restrict__ in, double *__restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    out[i] = static_cast<double>(in[i]);
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256) k_scale(int64_t n, Real *p, Real inv) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

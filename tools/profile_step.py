@@ -34,8 +34,12 @@ if args.families:
     t.set_profiling(True)
 ms = t.timed_steps(args.sweeps)
 if args.families:
-    for fam, name in enumerate(("column_sweeps", "q_init", "e_refresh")):
+    for fam, name in enumerate(("column_sweeps", "q_init", "e_refresh", "  stream level", "  gather level")):
         fms, n = t.kernel_ms(fam)
         print(f"  {name}: {fms / args.sweeps:.3f} ms/sweep in {n // args.sweeps} launch groups")
+    t.set_profiling(False)
+    t.timed_steps(2)  # captures the CUDA graphs
+    ms_graph = t.timed_steps(args.sweeps)
+    print(f"with CUDA-graph replay: {ms_graph / args.sweeps:.3f} ms/sweep")
 print(f"sweep path = {t.sweep_path()}")
 print(f"{args.sweeps} sweeps: {ms / args.sweeps:.2f} ms/sweep, launches={t.launch_count()}")
