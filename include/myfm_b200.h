@@ -107,6 +107,7 @@ typedef struct myfm_engine_options {
 
 typedef struct myfm_trainer myfm_trainer_t;
 typedef struct myfm_dataset myfm_dataset_t;
+typedef struct myfm_sample myfm_sample_t; /* one posterior sample resident on the device */
 
 const char *myfm_last_error(void);
 /* Library / device probe: writes the number of usable CUDA devices; never fails without a GPU. */
@@ -199,6 +200,20 @@ int myfm_predict_oprobit_mean(const myfm_dataset_t *d, int32_t n_samples, const 
                               const double *ws, const double *Vs, const double *cutpoints,
                               int32_t n_cpt, int64_t dim_all, int32_t rank, double *out);
 
+/* Kept samples that never leave the device.  GibbsFMTrainer::learn_with_callback copies the FM into
+ * the predictor for each of the last n_kept_samples iterations (FMTrainer.hpp:74-76);
+ * myfm_trainer_snapshot is that copy, device to device.  myfm_sample_get reads it back (any of
+ * w0 / w / V may be NULL; V is [dim_all x rank] row-major).  myfm_predict_samples_mean is
+ * Predictor::predict / predict_parallel / predict_parallel_oprobit (predictor.hpp:35-147) over such
+ * samples: n_cpt < 0 for regression / classification, else cutpoints is [n_samples x n_cpt] and out
+ * is [n_rows x (n_cpt + 1)]. */
+int myfm_trainer_snapshot(myfm_trainer_t *t, myfm_sample_t **out);
+void myfm_sample_destroy(myfm_sample_t *s);
+int myfm_sample_get(const myfm_sample_t *s, double *w0, double *w, double *V);
+int myfm_predict_samples_mean(const myfm_dataset_t *d, int32_t task_type, int32_t n_samples,
+                              myfm_sample_t *const *samples, const double *cutpoints, int32_t n_cpt,
+                              double *out);
+
 /* FM::predict_score with the trainer's CURRENT device-resident sample (no weight upload); used
  * by per-iteration callbacks (src/myfm/utils/callbacks/libfm.py:82-113). */
 int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, double *out);
@@ -219,6 +234,12 @@ int myfm_level_schedule(const myfm_csr_t *X, int32_t *level, int32_t *n_levels);
  * element-wise MAX all-reduce until nothing changes; the fixed point is the schedule of the
  * global matrix.  *changed = 1 when any entry grew. */
 int myfm_level_relax(const myfm_csr_t *X, int32_t *level, int32_t *n_levels, int32_t *changed);
+/* Test hooks for the host-side data preparation of myfm_trainer_create (csrc/host_data.hpp; no
+ * GPU needed).  myfm_host_transpose: the CSC arrays of X (entries of a column in ascending row
+ * order, BaseFMTrainer.hpp:61), indptr_out [n_cols + 1], indices_out / data_out [nnz].
+ * myfm_set_host_threads: number of threads the preparation passes use (0 = default). */
+int myfm_host_transpose(const myfm_csr_t *X, int64_t *indptr_out, int32_t *indices_out, double *data_out);
+int myfm_set_host_threads(int32_t n);
 /* ncclGetUniqueId for the row-sharded trainer: rank 0 calls it and ships the 128 bytes to the
  * other ranks by any side channel (myfm_b200/distributed.py uses torch.distributed). */
 int myfm_nccl_unique_id(void *out128);

@@ -92,7 +92,8 @@ EXPORTS = [
     "myfm_trainer_sweep_path", "myfm_trainer_launch_count", "myfm_trainer_kernel_ms", "myfm_trainer_set_profiling",
     "myfm_dataset_create", "myfm_dataset_destroy", "myfm_predict_score", "myfm_predict_mean",
     "myfm_predict_oprobit_mean", "myfm_trainer_predict_score", "myfm_rng_fill",
-    "myfm_level_schedule", "myfm_level_relax", "myfm_nccl_unique_id",
+    "myfm_trainer_snapshot", "myfm_sample_destroy", "myfm_sample_get", "myfm_predict_samples_mean",
+    "myfm_level_schedule", "myfm_level_relax", "myfm_host_transpose", "myfm_set_host_threads", "myfm_nccl_unique_id",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -111,6 +112,8 @@ def lib() -> C.CDLL:
         L.myfm_last_error.restype = C.c_char_p
         L.myfm_trainer_destroy.restype = None
         L.myfm_dataset_destroy.restype = None
+        L.myfm_sample_destroy.restype = None
+        L.myfm_sample_destroy.argtypes = [C.c_void_p]
         L.myfm_predict_score.argtypes = [
             C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.myfm_predict_mean.argtypes = [

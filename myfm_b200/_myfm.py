@@ -401,6 +401,74 @@ class _LiveFM(FM):
         return (FM, self.freeze().__getstate__())
 
 
+class _DeviceFM(FM):
+    """A kept sample (`Predictor.samples[i]`) that stays on the device: the copy the reference makes
+    per kept iteration (FMTrainer.hpp:74-76) is device-to-device here.  `w` / `V` are downloaded on
+    first access; prediction over such samples runs without any weight upload.  Pickles as a
+    plain FM."""
+
+    def __init__(self, handle: int, w0: float, cutpoints: List[np.ndarray], dim_all: int, rank: int,
+                 dtype: str, device: int) -> None:  # noqa: super().__init__ not wanted
+        self._h = C.c_void_p(handle)
+        self.w0 = float(w0)
+        self.cutpoints = cutpoints
+        self._dim_all, self._rank, self._dtype, self._device = int(dim_all), int(rank), dtype, int(device)
+        self._w: Optional[np.ndarray] = None
+        self._V: Optional[np.ndarray] = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().myfm_sample_destroy(h)
+            except Exception:
+                pass
+
+    def _materialize(self) -> None:
+        if self._w is None:
+            w = np.empty(self._dim_all, dtype=np.float64)
+            V = np.empty((self._dim_all, self._rank), dtype=np.float64)
+            _lib.check(_lib.lib().myfm_sample_get(self._h, None, _lib.vptr(w), _lib.vptr(V)))
+            self._w, self._V = w, V
+
+    @property
+    def w(self) -> np.ndarray:
+        self._materialize()
+        return self._w
+
+    @property
+    def V(self) -> np.ndarray:
+        self._materialize()
+        return self._V
+
+    def _on_device_for(self, opts) -> bool:
+        return self._h is not None and opts.dtype == self._dtype and opts.device == self._device
+
+    def predict_score(self, X, relations: Sequence[RelationBlock] = ()) -> np.ndarray:
+        opts = get_options()
+        if not self._on_device_for(opts):
+            return FM(self.w0, self.w, self.V, self.cutpoints).predict_score(X, relations)
+        X = _as_csr(X)
+        for rel in relations:
+            if X.shape[0] != rel.mapper_size:
+                raise ValueError("Relation blocks have inconsistent mapper size with case_size")
+        ds = _device_dataset(X, list(relations))
+        out = np.empty(X.shape[0], dtype=np.float64)
+        handles = (C.c_void_p * 1)(self._h)
+        _lib.check(_lib.lib().myfm_predict_samples_mean(ds._h, C.c_int32(int(TaskType.REGRESSION)), C.c_int32(1),
+                                                       handles, None, C.c_int32(-1), _lib.vptr(out)))
+        return out
+
+    def oprobit_predict_proba(self, X, relations, cutpoint_index: int) -> np.ndarray:
+        return FM(self.w0, self.w, self.V, self.cutpoints).oprobit_predict_proba(X, relations, cutpoint_index)
+
+    def __getstate__(self):
+        return (self.w0, self.w, self.V, self.cutpoints)
+
+    def __reduce__(self):
+        return (FM, (self.w0, self.w, self.V, self.cutpoints))
+
+
 # ------------------------------------------------------------------------------------------------
 # FMHyperParameters — declare_module.hpp:238-261, include/myfm/HyperParams.hpp
 # ------------------------------------------------------------------------------------------------
@@ -446,6 +514,14 @@ class Predictor:
                 given, self._feature_size))
         return X
 
+    def _device_handles(self):
+        """ctypes array of the samples' device handles when every sample lives on the device the
+        current engine options name, in their compute dtype; else None (host path)."""
+        opts = get_options()
+        if not all(isinstance(s, _DeviceFM) and s._on_device_for(opts) for s in self.samples):
+            return None
+        return (C.c_void_p * len(self.samples))(*[s._h for s in self.samples])
+
     def _stack(self):
         w0s = np.asarray([s.w0 for s in self.samples], dtype=np.float64)
         ws = np.ascontiguousarray(np.stack([s.w for s in self.samples]), dtype=np.float64)
@@ -457,8 +533,14 @@ class Predictor:
         if not self.samples:
             raise RuntimeError(empty_message)
         ds = _device_dataset(X, list(relations))
-        w0s, ws, Vs = self._stack()
         out = np.empty(X.shape[0], dtype=np.float64)
+        handles = self._device_handles()
+        if handles is not None:
+            _lib.check(_lib.lib().myfm_predict_samples_mean(
+                ds._h, C.c_int32(int(self._type)), C.c_int32(len(self.samples)), handles, None, C.c_int32(-1),
+                _lib.vptr(out)))
+            return out
+        w0s, ws, Vs = self._stack()
         _lib.check(_lib.lib().myfm_predict_mean(
             ds._h, C.c_int32(int(self._type)), C.c_int32(len(self.samples)), _lib.vptr(w0s),
             _lib.vptr(ws), _lib.vptr(Vs), C.c_int64(self._feature_size), C.c_int32(self._rank),
@@ -485,8 +567,14 @@ class Predictor:
         cps = np.ascontiguousarray(
             np.stack([s.cutpoints[cutpoint_index] for s in self.samples]), dtype=np.float64)
         ds = _device_dataset(X, list(relations))
-        w0s, ws, Vs = self._stack()
         out = np.empty((X.shape[0], cps.shape[1] + 1), dtype=np.float64)
+        handles = self._device_handles()
+        if handles is not None:
+            _lib.check(_lib.lib().myfm_predict_samples_mean(
+                ds._h, C.c_int32(int(TaskType.ORDERED)), C.c_int32(len(self.samples)), handles, _lib.vptr(cps),
+                C.c_int32(cps.shape[1]), _lib.vptr(out)))
+            return out
+        w0s, ws, Vs = self._stack()
         _lib.check(_lib.lib().myfm_predict_oprobit_mean(
             ds._h, C.c_int32(len(self.samples)), _lib.vptr(w0s), _lib.vptr(ws), _lib.vptr(Vs),
             _lib.vptr(cps), C.c_int32(cps.shape[1]), C.c_int64(self._feature_size),
@@ -537,6 +625,7 @@ class _TrainerHandle:
         rels = _lib.RelationsHolder(relations)
         eo = _lib.EngineOptions()
         eo.dtype, eo.rng, eo.device = _lib.DTYPES[opts.dtype], _lib.RNGS[opts.rng], opts.device
+        self.dtype, self.device = opts.dtype, opts.device
         eo.world_size, eo.rank = opts.world_size, opts.rank
         eo.row_offset, eo.n_rows_global = opts.row_offset, opts.n_rows_global or X.shape[0]
         uid = (C.c_char * 128).from_buffer_copy(opts.nccl_unique_id) if opts.nccl_unique_id else None
@@ -592,6 +681,18 @@ class _TrainerHandle:
                 _lib.check(_lib.lib().myfm_trainer_get_cutpoints(self._h, C.c_int32(g), _lib.vptr(a)))
                 cps.append(a)
         return w0.value, w, V, cps
+
+    def snapshot(self) -> "_DeviceFM":
+        """The current sample, copied device to device (the kept-sample copy of FMTrainer.hpp:74-76)."""
+        h = C.c_void_p()
+        _lib.check(_lib.lib().myfm_trainer_snapshot(self._h, C.byref(h)))
+        cps = []
+        if self.task_type == TaskType.ORDERED:
+            for g, size in enumerate(self.cutpoint_sizes):
+                a = np.empty(size, dtype=np.float64)
+                _lib.check(_lib.lib().myfm_trainer_get_cutpoints(self._h, C.c_int32(g), _lib.vptr(a)))
+                cps.append(a)
+        return _DeviceFM(h.value, self.get_w0(), cps, self.dim_all, self.rank, self.dtype, self.device)
 
     def get_w0(self) -> float:
         w0 = C.c_double()
@@ -707,7 +808,7 @@ def create_train_fm(
         trainer.step(1)
         live = _LiveFM(trainer)
         if n_iter <= it + n_kept:
-            predictor.samples.append(live.freeze())
+            predictor.samples.append(trainer.snapshot())
         hyper = trainer.get_hyper()
         history.hypers.append(hyper)
         if callback(it, live, hyper, history):

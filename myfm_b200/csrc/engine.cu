@@ -336,6 +336,32 @@ template <typename Real> struct Dataset : DatasetBase {
 // ------------------------------------------------------------------------------------------------
 // Trainer
 // ------------------------------------------------------------------------------------------------
+// One posterior sample kept on the device (the FM copy GibbsFMTrainer keeps per kept iteration,
+// FMTrainer.hpp:74-76): w0, w and the feature-major V, in the trainer's compute dtype.
+struct SampleBase {
+  virtual ~SampleBase() = default;
+  virtual void get(double *w0, double *w, double *V) = 0;
+  int dtype = MYFM_DTYPE_F32, device = 0, K = 0;
+  int64_t dim_all = 0;
+};
+template <typename Real> struct Sample : SampleBase {
+  DevBuf<Real> w0, w, Vt;
+  void get(double *w0_out, double *w_out, double *V_out) override {
+    MYFM_CUDA(cudaSetDevice(device));
+    auto pull = [&](const DevBuf<Real> &buf, size_t n, double *out) {
+      if (!out || !n)
+        return;
+      std::vector<Real> h(n);
+      MYFM_CUDA(cudaMemcpy(h.data(), buf.p, n * sizeof(Real), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; i++)
+        out[i] = h[i];
+    };
+    pull(w0, 1, w0_out);
+    pull(w, dim_all, w_out);
+    pull(Vt, static_cast<size_t>(dim_all) * K, V_out);
+  }
+};
+
 struct TrainerBase {
   virtual ~TrainerBase() = default;
   virtual void init_fm(int rank, double init_std) = 0;
@@ -355,6 +381,7 @@ struct TrainerBase {
                          const double *lambda_V, const double *e) = 0;
   virtual int64_t launch_count() const = 0;
   virtual int sweep_path() const = 0;
+  virtual std::unique_ptr<SampleBase> snapshot() = 0;
   virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
   virtual void set_profiling(bool on) = 0;
   virtual void predict_score(DatasetBase *d, double *out) = 0;
@@ -1732,6 +1759,20 @@ template <typename Real> struct Trainer : TrainerBase {
   }
   int64_t launch_count() const override { return launches; }
   int sweep_path() const override { return field_path ? 1 : 0; }
+  std::unique_ptr<SampleBase> snapshot() override { // device-to-device copy of the current sample
+    require_fm();
+    MYFM_CUDA(cudaSetDevice(device));
+    auto sm = std::make_unique<Sample<Real>>();
+    sm->dtype = dtype, sm->device = device, sm->K = K, sm->dim_all = D_all;
+    sm->w0.alloc(1), sm->w.alloc(D_all), sm->Vt.alloc(static_cast<size_t>(D_all) * K);
+    MYFM_CUDA(cudaMemcpyAsync(sm->w0.p, hv().w0, sizeof(Real), cudaMemcpyDeviceToDevice, stream));
+    if (D_all)
+      MYFM_CUDA(cudaMemcpyAsync(sm->w.p, w.p, D_all * sizeof(Real), cudaMemcpyDeviceToDevice, stream));
+    if (sm->Vt.n)
+      MYFM_CUDA(cudaMemcpyAsync(sm->Vt.p, Vt.p, sm->Vt.n * sizeof(Real), cudaMemcpyDeviceToDevice, stream));
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    return sm;
+  }
   void kernel_ms(int family, double *ms, int64_t *n) override {
     sync();
     if (family < 0 || family >= KernelTimer::FAMILIES)
@@ -1827,6 +1868,55 @@ void dataset_predict_mean(Dataset<Real> &d, int task, int n_samples, const doubl
     out[i] = h[i];
 }
 
+// The same mean over samples that already live on the device: no staging.
+template <typename Real>
+void dataset_predict_mean_samples(Dataset<Real> &d, int task, int n_samples, SampleBase *const *samples,
+                                  const double *cutpoints, int n_cpt, double *out) {
+  if (n_samples <= 0)
+    throw std::runtime_error("Told to predict but no sample available.");
+  MYFM_CUDA(cudaSetDevice(d.device));
+  const bool ordered = n_cpt >= 0;
+  const size_t width = ordered ? n_cpt + 1 : 1;
+  const int n = static_cast<int>(d.n_rows);
+  if (d.score.n < static_cast<size_t>(n))
+    d.score.alloc(n);
+  d.accum.alloc(static_cast<size_t>(n) * width);
+  d.accum.zero(d.stream);
+  for (int s = 0; s < n_samples; s++) {
+    if (!samples[s] || samples[s]->dtype != d.dtype || samples[s]->device != d.device)
+      throw std::invalid_argument("sample and dataset differ in compute dtype or device.");
+    auto *sm = static_cast<Sample<Real> *>(samples[s]);
+    d.check_dim(sm->dim_all);
+    d.predict(sm->w.p, sm->Vt.p, sm->K, sm->w0.p, nullptr, d.score.p);
+    if (!n)
+      continue;
+    if (ordered) {
+      std::vector<Real> cp(n_cpt);
+      for (int c = 0; c < n_cpt; c++)
+        cp[c] = static_cast<Real>(cutpoints[static_cast<size_t>(s) * n_cpt + c]);
+      MYFM_CUDA(cudaStreamSynchronize(d.stream)); // the previous sample's kernel still reads cutp
+      d.cutp.upload(cp, d.stream);
+      MYFM_CUDA(cudaStreamSynchronize(d.stream));
+      k_accumulate_oprobit<Real><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.cutp.p, n_cpt, d.accum.p);
+    } else if (task == MYFM_TASK_CLASSIFICATION) {
+      k_accumulate<Real, 1><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.accum.p);
+    } else if (task == MYFM_TASK_REGRESSION) {
+      k_accumulate<Real, 0><<<ceil_div(n, 256), 256, 0, d.stream>>>(n, d.score.p, d.accum.p);
+    }
+    d.count();
+  }
+  if (n) {
+    k_scale<Real><<<ceil_div(static_cast<int64_t>(n) * width, 256), 256, 0, d.stream>>>(
+        static_cast<int64_t>(n) * width, d.accum.p, static_cast<Real>(n_samples));
+    d.count();
+  }
+  std::vector<Real> h(static_cast<size_t>(n) * width);
+  d.accum.download(h.data(), h.size(), d.stream);
+  MYFM_CUDA(cudaStreamSynchronize(d.stream));
+  for (size_t i = 0; i < h.size(); i++)
+    out[i] = h[i];
+}
+
 } // namespace myfm
 
 // ------------------------------------------------------------------------------------------------
@@ -1839,6 +1929,9 @@ struct myfm_trainer {
 };
 struct myfm_dataset {
   std::unique_ptr<DatasetBase> impl;
+};
+struct myfm_sample {
+  std::unique_ptr<SampleBase> impl;
 };
 
 #define MYFM_API_BEGIN try {
@@ -2089,6 +2182,41 @@ int myfm_predict_oprobit_mean(const myfm_dataset_t *d, int32_t n_samples, const 
   MYFM_API_END
 }
 
+int myfm_trainer_snapshot(myfm_trainer_t *t, myfm_sample_t **out) {
+  MYFM_API_BEGIN
+  require(t, "trainer"), require(out, "out");
+  auto holder = std::make_unique<myfm_sample>();
+  holder->impl = t->impl->snapshot();
+  *out = holder.release();
+  MYFM_API_END
+}
+void myfm_sample_destroy(myfm_sample_t *s) { delete s; }
+int myfm_sample_get(const myfm_sample_t *s, double *w0, double *w, double *V) {
+  MYFM_API_BEGIN
+  require(s, "sample");
+  s->impl->get(w0, w, V);
+  MYFM_API_END
+}
+int myfm_predict_samples_mean(const myfm_dataset_t *d, int32_t task_type, int32_t n_samples,
+                              myfm_sample_t *const *samples, const double *cutpoints, int32_t n_cpt, double *out) {
+  MYFM_API_BEGIN
+  require(d, "dataset"), require(samples, "samples");
+  if (task_type == MYFM_TASK_ORDERED && n_cpt >= 0)
+    require(cutpoints, "cutpoints");
+  std::vector<SampleBase *> impls(std::max(0, n_samples));
+  for (int i = 0; i < n_samples; i++) {
+    require(samples[i], "sample");
+    impls[i] = samples[i]->impl.get();
+  }
+  if (d->impl->dtype == MYFM_DTYPE_F32)
+    dataset_predict_mean_samples(*static_cast<Dataset<float> *>(d->impl.get()), task_type, n_samples, impls.data(),
+                                 cutpoints, n_cpt, out);
+  else
+    dataset_predict_mean_samples(*static_cast<Dataset<double> *>(d->impl.get()), task_type, n_samples, impls.data(),
+                                 cutpoints, n_cpt, out);
+  MYFM_API_END
+}
+
 int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, double *out) {
   MYFM_API_BEGIN
   require(t, "trainer"), require(d, "dataset");
@@ -2119,6 +2247,22 @@ int myfm_rng_fill(int32_t dtype, int32_t seed, int64_t n_skip_normals_persistent
     run(float{});
   else
     run(double{});
+  MYFM_API_END
+}
+
+int myfm_host_transpose(const myfm_csr_t *X, int64_t *indptr_out, int32_t *indices_out, double *data_out) {
+  MYFM_API_BEGIN
+  require(X, "X"), require(indptr_out, "indptr_out");
+  HostCs<double> t = host_transpose(host_from_api<double>(*X, "X"));
+  for (size_t i = 0; i < t.ptr.size(); i++)
+    indptr_out[i] = t.ptr[i];
+  for (size_t i = 0; i < t.idx.size(); i++)
+    indices_out[i] = t.idx[i], data_out[i] = t.val[i];
+  MYFM_API_END
+}
+int myfm_set_host_threads(int32_t n) {
+  MYFM_API_BEGIN
+  host_threads_override().store(n > 0 ? n : 0);
   MYFM_API_END
 }
 

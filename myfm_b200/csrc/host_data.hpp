@@ -6,7 +6,11 @@
 #include "../../include/myfm_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <cstdlib>
+#include <exception>
+#include <thread>
 #include <limits>
 #include <sstream>
 #include <stdexcept>
@@ -15,6 +19,50 @@
 #include <vector>
 
 namespace myfm {
+
+// Host-side data preparation is a handful of O(nnz) passes; they run on a few threads
+// (MYFM_HOST_THREADS, default min(16, hardware threads)).  fn(part, n_parts) is called once per part.
+inline std::atomic<int> &host_threads_override() {
+  static std::atomic<int> v{0};
+  return v;
+}
+inline int host_threads() {
+  static const int n = [] {
+    const char *env = std::getenv("MYFM_HOST_THREADS");
+    int v = env ? std::atoi(env) : 0;
+    if (v <= 0)
+      v = static_cast<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    return v;
+  }();
+  const int o = host_threads_override().load();
+  return o > 0 ? o : n;
+}
+template <typename Fn> void parallel_parts(int n_parts, Fn fn) {
+  if (n_parts <= 1) {
+    fn(0, 1);
+    return;
+  }
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> errors(n_parts);
+  for (int t = 0; t < n_parts; t++)
+    pool.emplace_back([&, t] {
+      try {
+        fn(t, n_parts);
+      } catch (...) {
+        errors[t] = std::current_exception();
+      }
+    });
+  for (auto &th : pool)
+    th.join();
+  for (auto &e : errors)
+    if (e)
+      std::rethrow_exception(e);
+}
+// [begin, end) of part t when n items are cut into n_parts contiguous ranges
+inline std::pair<int64_t, int64_t> part_range(int64_t n, int t, int n_parts) {
+  return {n * t / n_parts, n * (t + 1) / n_parts};
+}
+inline int parts_for(int64_t work) { return (work < (1 << 18) && host_threads_override().load() <= 0) ? 1 : host_threads(); }
 
 template <typename Real> struct HostCs { // compressed sparse, major x minor
   int64_t n_major = 0, n_minor = 0;
@@ -37,18 +85,24 @@ template <typename Real> HostCs<Real> host_from_api(const myfm_csr_t &m, const c
                                 ": a shard must have fewer than 2^31 rows, columns and non-zeros.");
   out.ptr.resize(m.n_rows + 1);
   out.ptr[0] = 0;
-  for (int64_t r = 0; r < m.n_rows; r++) {
-    if (m.indptr[r + 1] < m.indptr[r])
-      throw std::invalid_argument(std::string(what) + ": indptr is not monotone.");
-    out.ptr[r + 1] = static_cast<int>(m.indptr[r + 1]);
-  }
-  out.idx.assign(m.indices, m.indices + nnz);
+  out.idx.resize(nnz);
   out.val.resize(nnz);
-  for (int64_t p = 0; p < nnz; p++) {
-    if (out.idx[p] < 0 || out.idx[p] >= m.n_cols)
-      throw std::invalid_argument(std::string(what) + ": column index out of range.");
-    out.val[p] = static_cast<Real>(m.data[p]);
-  }
+  parallel_parts(parts_for(nnz), [&](int t, int n_parts) {
+    auto [r0, r1] = part_range(m.n_rows, t, n_parts);
+    for (int64_t r = r0; r < r1; r++) {
+      if (m.indptr[r + 1] < m.indptr[r])
+        throw std::invalid_argument(std::string(what) + ": indptr is not monotone.");
+      out.ptr[r + 1] = static_cast<int>(m.indptr[r + 1]);
+    }
+    auto [p0, p1] = part_range(nnz, t, n_parts);
+    for (int64_t p = p0; p < p1; p++) {
+      const int j = m.indices[p];
+      if (j < 0 || j >= m.n_cols)
+        throw std::invalid_argument(std::string(what) + ": column index out of range.");
+      out.idx[p] = j;
+      out.val[p] = static_cast<Real>(m.data[p]);
+    }
+  });
   return out;
 }
 
@@ -59,19 +113,38 @@ template <typename Real> HostCs<Real> host_transpose(const HostCs<Real> &a) {
   t.n_major = a.n_minor;
   t.n_minor = a.n_major;
   t.ptr.assign(a.n_minor + 1, 0);
-  for (int c : a.idx)
-    t.ptr[c + 1]++;
-  for (int64_t c = 0; c < a.n_minor; c++)
-    t.ptr[c + 1] += t.ptr[c];
   t.idx.resize(a.idx.size());
   t.val.resize(a.val.size());
-  std::vector<int> cur(t.ptr.begin(), t.ptr.end() - 1);
-  for (int64_t r = 0; r < a.n_major; r++)
-    for (int p = a.ptr[r]; p < a.ptr[r + 1]; p++) {
-      int dst = cur[a.idx[p]]++;
-      t.idx[dst] = static_cast<int>(r);
-      t.val[dst] = a.val[p];
+  // counting sort by column; every part owns a contiguous row range, so inside a column the
+  // entries stay in ascending row order whatever the number of parts
+  const int n_parts = a.n_minor > (1 << 22) ? 1 : parts_for(a.nnz());
+  std::vector<std::vector<int>> count(n_parts);
+  parallel_parts(n_parts, [&](int p, int np) {
+    auto [r0, r1] = part_range(a.n_major, p, np);
+    std::vector<int> &c = count[p];
+    c.assign(a.n_minor, 0);
+    for (int q = a.ptr[r0]; q < a.ptr[r1]; q++)
+      c[a.idx[q]]++;
+  });
+  for (int64_t c = 0; c < a.n_minor; c++) { // count[p][c] becomes the first slot of part p in column c
+    int at = t.ptr[c];
+    for (int p = 0; p < n_parts; p++) {
+      const int n = count[p][c];
+      count[p][c] = at;
+      at += n;
     }
+    t.ptr[c + 1] = at;
+  }
+  parallel_parts(n_parts, [&](int p, int np) {
+    auto [r0, r1] = part_range(a.n_major, p, np);
+    std::vector<int> &cur = count[p];
+    for (int64_t r = r0; r < r1; r++)
+      for (int q = a.ptr[r]; q < a.ptr[r + 1]; q++) {
+        const int dst = cur[a.idx[q]]++;
+        t.idx[dst] = static_cast<int>(r);
+        t.val[dst] = a.val[q];
+      }
+  });
   return t;
 }
 
@@ -228,19 +301,30 @@ std::vector<int> primary_row_order(const HostCs<Real> &csc, const std::vector<in
     if (level_nnz[l] > 0 && (best < 0 || level_nnz[l] > level_nnz[best]))
       best = l;
   *primary_level = best;
-  std::vector<int> perm;
-  perm.reserve(n_rows);
+  std::vector<int> perm(n_rows);
   std::vector<char> taken(n_rows, 0);
-  if (best >= 0)
+  int64_t n_primary = 0;
+  if (best >= 0) {
+    std::vector<int64_t> off(csc.n_major + 1, 0);
     for (int64_t j = 0; j < csc.n_major; j++)
-      if (level[j] == best)
-        for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++) {
-          perm.push_back(csc.idx[p]);
-          taken[csc.idx[p]] = 1;
+      off[j + 1] = off[j] + (level[j] == best ? csc.ptr[j + 1] - csc.ptr[j] : 0);
+    n_primary = off[csc.n_major];
+    parallel_parts(parts_for(n_primary), [&](int t, int n_parts) {
+      auto [j0, j1] = part_range(csc.n_major, t, n_parts);
+      for (int64_t j = j0; j < j1; j++)
+        if (level[j] == best) {
+          int64_t at = off[j];
+          for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++) {
+            perm[at++] = csc.idx[p];
+            taken[csc.idx[p]] = 1; // columns of a level are row-disjoint: no two parts touch one row
+          }
         }
+    });
+  }
+  int64_t at = n_primary;
   for (int64_t i = 0; i < n_rows; i++)
     if (!taken[i])
-      perm.push_back(static_cast<int>(i));
+      perm[at++] = static_cast<int>(i);
   return perm;
 }
 
@@ -252,12 +336,16 @@ HostCs<Real> permute_rows(const HostCs<Real> &csr, const std::vector<int> &perm)
   out.idx.resize(csr.idx.size());
   out.val.resize(csr.val.size());
   out.ptr[0] = 0;
-  for (int64_t i = 0; i < csr.n_major; i++) {
-    const int src = perm[i], b = csr.ptr[src], n = csr.ptr[src + 1] - b, dst = out.ptr[i];
-    std::copy(csr.idx.begin() + b, csr.idx.begin() + b + n, out.idx.begin() + dst);
-    std::copy(csr.val.begin() + b, csr.val.begin() + b + n, out.val.begin() + dst);
-    out.ptr[i + 1] = dst + n;
-  }
+  for (int64_t i = 0; i < csr.n_major; i++)
+    out.ptr[i + 1] = out.ptr[i] + (csr.ptr[perm[i] + 1] - csr.ptr[perm[i]]);
+  parallel_parts(parts_for(csr.nnz()), [&](int t, int n_parts) {
+    auto [i0, i1] = part_range(csr.n_major, t, n_parts);
+    for (int64_t i = i0; i < i1; i++) {
+      const int src = perm[i], b = csr.ptr[src], n = csr.ptr[src + 1] - b, dst = out.ptr[i];
+      std::copy(csr.idx.begin() + b, csr.idx.begin() + b + n, out.idx.begin() + dst);
+      std::copy(csr.val.begin() + b, csr.val.begin() + b + n, out.val.begin() + dst);
+    }
+  });
   return out;
 }
 

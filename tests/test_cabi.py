@@ -119,3 +119,29 @@ def test_engine_gamma_is_standardised(dtype):
     assert abs(g.mean() - 2.5) < 0.15 and abs(g.var() - 2.5) < 0.5
     big = rng_fill(dtype, 7, 0, [1] * 200, [5.0e6] * 200)
     assert abs(big.mean() / 5.0e6 - 1) < 1e-3
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_host_transpose_threads(threads):
+    """The multi-threaded counting sort of the setup (csrc/host_data.hpp) against scipy: columns
+    list their rows in ascending order whatever the number of threads (BaseFMTrainer.hpp:61)."""
+    rng = np.random.default_rng(threads)
+    X = sps.random(5000, 300, 0.02, format="csr", random_state=int(rng.integers(1 << 30)))
+    X.sort_indices()
+    from myfm_b200 import _lib
+
+    h = _lib.CsrHolder(X)
+    indptr = np.empty(X.shape[1] + 1, dtype=np.int64)
+    indices = np.empty(X.nnz, dtype=np.int32)
+    data = np.empty(X.nnz, dtype=np.float64)
+    _lib.check(_lib.lib().myfm_set_host_threads(C.c_int32(threads)))
+    try:
+        _lib.check(_lib.lib().myfm_host_transpose(C.byref(h.struct), _lib.vptr(indptr), _lib.vptr(indices),
+                                                  _lib.vptr(data)))
+    finally:
+        _lib.check(_lib.lib().myfm_set_host_threads(C.c_int32(0)))
+    ref = X.tocsc()
+    ref.sort_indices()
+    np.testing.assert_array_equal(indptr, ref.indptr)
+    np.testing.assert_array_equal(indices, ref.indices)
+    np.testing.assert_array_equal(data, ref.data)
