@@ -424,7 +424,9 @@ template <typename Real> struct Trainer : TrainerBase {
   bool f_pending_valid = false; // the last level's draw of the previous vector awaits the next pass
   SweepLevel f_level0, f_levelL;
   DevBuf<SweepItem> f_items0, f_itemsL;
-  DevBuf<int> f_seg_countL, f_tail_idx, f_sched, f_chunk_done;
+  DevBuf<int> f_seg_countL, f_tail_idx, f_sched, f_chunk_done, f_item_slot0, f_item_slotL, f_colsL;
+  DevBuf<Real> f_colstat; // row shards: column statistics of a level, summed over the ranks
+  int f_ncols0 = 0, f_ncolsL = 0;
   DevBuf<Real> f_tail_val, f_own_val, f_pend_told, f_pend_tnew, f_partial;
 
   int64_t N = 0, D = 0, D_all = 0;
@@ -677,6 +679,15 @@ template <typename Real> struct Trainer : TrainerBase {
       ncclUniqueId id;
       std::memcpy(&id, o.nccl_unique_id, sizeof(id));
       nccl.check(nccl.CommInitRank(&comm, world, id, o.rank), "ncclCommInitRank");
+      // every rank must take the same schedule: the field path only if every shard qualifies
+      DevBuf<int> flag(1);
+      const int mine = field_path ? 1 : 0;
+      flag.upload(&mine, 1, stream);
+      nccl.check(nccl.AllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, comm, stream), "ncclAllReduce");
+      int all = 0;
+      flag.download(&all, 1, stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+      field_path = all != 0;
     }
     // Gamma shapes are data independent (FMTrainer.hpp:140,157)
     shape_alpha = (static_cast<Real>(cfg.alpha_0) + N_global) / 2;
@@ -752,7 +763,7 @@ template <typename Real> struct Trainer : TrainerBase {
       use_graphs = !(no_graph && no_graph[0] == '1');
     }
     if (field_path)
-      f_sched.alloc(static_cast<size_t>(K) + 2);
+      f_sched.alloc(2 * (static_cast<size_t>(K) + 2));
     setup_rng();
     const bool ordered = cfg.task_type == MYFM_TASK_ORDERED;
     data.predict(w.p, Vt.p, K, hv().w0, ordered ? nullptr : y.p, e_ptr(), 2);
@@ -1031,8 +1042,7 @@ template <typename Real> struct Trainer : TrainerBase {
       return;
     const int L = main_row_len;
     const int64_t n = Xh.n_major;
-    if (world > 1 || n_rel > 0 || n == 0 || L < 2 || L != n_levels || plan.primary_level != 0 ||
-        !plan.levels[0].contig)
+    if (n_rel > 0 || n == 0 || L < 2 || L != n_levels || plan.primary_level != 0 || !plan.levels[0].contig)
       return;
     for (int64_t i = 0; i < n; i++)
       for (int k = 0; k < L; k++)
@@ -1095,6 +1105,21 @@ template <typename Real> struct Trainer : TrainerBase {
       f_tail_val.upload(tv, stream);
       f_own_val.upload(ov, stream);
     }
+    if (world > 1) { // column slots and the statistics buffer of the two-pass schedule
+      f_item_slot0.upload(p0.item_slot, stream);
+      f_item_slotL.upload(pL.item_slot, stream);
+      std::vector<int> colsL;
+      f_ncols0 = 0;
+      for (int64_t j = 0; j < Xth.n_major; j++) {
+        if (level[j] == 0)
+          f_ncols0++;
+        if (level[j] == L - 1)
+          colsL.push_back(static_cast<int>(j));
+      }
+      f_ncolsL = static_cast<int>(colsL.size());
+      f_colsL.upload(colsL, stream);
+      f_colstat.alloc(2 * static_cast<size_t>(std::max(f_ncols0, f_ncolsL)));
+    }
     f_pend_told.alloc(f_tab);
     f_pend_tnew.alloc(f_tab);
     f_pend_told.zero(stream);
@@ -1103,15 +1128,24 @@ template <typename Real> struct Trainer : TrainerBase {
     field_path = true;
   }
 
-  template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a) {
+  template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a, int mode) {
     if (IS_V && f_tail > 1)
-      launch_field_stream_as<IS_V, UNIT, true, PEND>(a);
+      launch_field_stream_mid<IS_V, UNIT, true, PEND>(a, mode);
     else
-      launch_field_stream_as<IS_V, UNIT, false, PEND>(a);
+      launch_field_stream_mid<IS_V, UNIT, false, PEND>(a, mode);
   }
   template <bool IS_V, bool UNIT, bool HAS_MID, int PEND>
+  void launch_field_stream_mid(const FieldStreamArgs<Real> &a, int mode) {
+    if (mode == FIELD_FUSED)
+      launch_field_stream_as<IS_V, UNIT, HAS_MID, PEND, FIELD_FUSED>(a);
+    else if (mode == FIELD_STATS)
+      launch_field_stream_as<IS_V, UNIT, HAS_MID, PEND, FIELD_STATS>(a);
+    else
+      launch_field_stream_as<IS_V, UNIT, HAS_MID, PEND, FIELD_UPDATE>(a);
+  }
+  template <bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE>
   void launch_field_stream_as(const FieldStreamArgs<Real> &a) {
-    auto kernel = k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND>;
+    auto kernel = k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND, MODE>;
     const size_t smem = 3 * static_cast<size_t>(f_tab) * sizeof(Real);
     static size_t configured = 0; // per instantiation
     if (smem > configured) {
@@ -1134,7 +1168,6 @@ template <typename Real> struct Trainer : TrainerBase {
       FieldStreamArgs<Real> a;
       a.item = reinterpret_cast<const int4 *>(f_items0.p + f_level0.s0);
       a.nCC = f_nCC, a.nCR = f_nCR, a.nG = f_nG, a.nW = f_nW;
-      a.sched = f_sched.p + (f_launch++);
       a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
       a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;
       a.tail_last = f_tail_idx.p + static_cast<int64_t>(f_tail - 1) * N;
@@ -1143,21 +1176,29 @@ template <typename Real> struct Trainer : TrainerBase {
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
       a.last_base = f_last_base, a.n_tab = f_tab;
       a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
+      a.item_slot = f_item_slot0.p + f_level0.s0, a.colstat = f_colstat.p;
 #define MYFM_FS(V, P)                                                                              \
   if (main_unit)                                                                                   \
-    launch_field_stream<V, true, P>(a);                                                            \
+    launch_field_stream<V, true, P>(a, mode);                                                      \
   else                                                                                             \
-    launch_field_stream<V, false, P>(a);
-      if (!IS_V) {
-        if (pend != PEND_NONE)
-          throw std::logic_error("field path: the w sweep must not find a pending update.");
-        MYFM_FS(false, PEND_NONE)
-      } else if (pend == PEND_NONE) {
-        MYFM_FS(true, PEND_NONE)
-      } else if (pend == PEND_W) {
-        MYFM_FS(true, PEND_W)
-      } else {
-        MYFM_FS(true, PEND_V)
+    launch_field_stream<V, false, P>(a, mode);
+      // one GPU: one fused pass.  Row shards: statistics, all-reduce over the ranks, update.
+      for (int pass = 0; pass < (world > 1 ? 2 : 1); pass++) {
+        const int mode = world > 1 ? (pass == 0 ? FIELD_STATS : FIELD_UPDATE) : FIELD_FUSED;
+        a.sched = f_sched.p + (f_launch++);
+        if (!IS_V) {
+          if (pend != PEND_NONE)
+            throw std::logic_error("field path: the w sweep must not find a pending update.");
+          MYFM_FS(false, PEND_NONE)
+        } else if (pend == PEND_NONE) {
+          MYFM_FS(true, PEND_NONE)
+        } else if (pend == PEND_W) {
+          MYFM_FS(true, PEND_W)
+        } else {
+          MYFM_FS(true, PEND_V)
+        }
+        if (mode == FIELD_STATS)
+          allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncols0));
       }
 #undef MYFM_FS
     }
@@ -1174,6 +1215,7 @@ template <typename Real> struct Trainer : TrainerBase {
       a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
       a.partial = f_partial.p, a.chunk_done = f_chunk_done.p, a.last_base = f_last_base;
+      a.item_slot = f_item_slotL.p + f_levelL.s0, a.colstat = world > 1 ? f_colstat.p : nullptr;
       a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
       const int grid = a.nS + a.nC + ceil_div(a.nW, STATS_THREADS / 32);
       if (grid) {
@@ -1181,6 +1223,11 @@ template <typename Real> struct Trainer : TrainerBase {
           k_field_stats<Real, IS_V, true><<<grid, STATS_THREADS, 0, stream>>>(a);
         else
           k_field_stats<Real, IS_V, false><<<grid, STATS_THREADS, 0, stream>>>(a);
+        launched();
+      }
+      if (world > 1) { // statistics of this rank's rows -> sum over the ranks -> identical draw everywhere
+        allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncolsL));
+        k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, f_colsL.p, f_ncolsL);
         launched();
       }
     }

@@ -58,7 +58,17 @@ template <typename Real> struct FieldStreamArgs {
   const Real *alpha, *lambda, *mu;
   int last_base, n_tab; // the last level's columns are [last_base, last_base + n_tab)
   const Real *pend_told, *pend_tnew; // [n_tab] draw left pending by the previous vector
+  // row-sharded training (FIELD_STATS / FIELD_UPDATE): statistics of every level-0 column, summed
+  // over the ranks between the two passes
+  const int *item_slot; // column slot of every item (same numbering on every rank)
+  Real *colstat;        // [2 * columns of level 0]
 };
+
+// One GPU: FIELD_FUSED (statistics, draw and update in one pass).  Row shards: the rows of a column
+// live on several GPUs, so the pass runs twice around an all-reduce of the column statistics —
+// FIELD_STATS leaves (sum h^2, sum -e h) per column, FIELD_UPDATE draws from the summed statistics
+// (identically on every rank) and writes e, q.
+enum { FIELD_FUSED = 0, FIELD_STATS = 1, FIELD_UPDATE = 2 };
 
 // U rows of the streaming pass in flight per thread: all global loads are issued first (load),
 // the shared-memory lookups and the arithmetic follow (finish) — a row's table index comes out of
@@ -200,11 +210,12 @@ __device__ __forceinline__ void field_group_sum(Real &sq, Real &lin, Real *s_par
 // in registers between the reduction and the update, so every row is read once and written once.
 // FULL: slots 0 .. NS-2 hold a row in every thread (the caller picked NS = ceil(rows / threads)),
 // only the last slot is ragged; otherwise every slot is checked.
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int GW, int NS, bool FULL>
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW, int NS, bool FULL>
 __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a, const Real *s_told,
                                                   const Real *s_tnew, const Real *s_tnext, int4 it, int t,
                                                   Real theta_old, Real alpha, Real lam, Real mu, Real z,
-                                                  Real *s_part, int parity, int grp, int wig, int lane) {
+                                                  Real *s_part, int parity, int grp, int wig, int lane,
+                                                  Real theta_given, Real &sq, Real &lin) {
   constexpr int NT = 32 * GW;
   FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, NS> b;
   Real e[NS], q[NS], x0[NS];
@@ -215,15 +226,19 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
     ok[s] = (FULL && s < NS - 1) || i0 + NT * s < it.z;
     b.load(a, s, ok[s] ? i0 + NT * s : it.z - 1);
   }
-  Real sq = 0, lin = 0;
+  sq = 0, lin = 0;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
     b.finish(a, s_told, s_tnew, s_tnext, s, ok[s] ? i0 + NT * s : it.z - 1, theta_old, e[s], q[s], x0[s]);
-    if (ok[s])
+    if (MODE != FIELD_UPDATE && ok[s])
       field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
   }
-  field_group_sum<Real, GW>(sq, lin, s_part, parity, grp, wig, lane);
-  const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+  if (MODE != FIELD_UPDATE)
+    field_group_sum<Real, GW>(sq, lin, s_part, parity, grp, wig, lane);
+  if (MODE == FIELD_STATS)
+    return theta_old;
+  const Real theta_new =
+      MODE == FIELD_UPDATE ? theta_given : column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
 #pragma unroll
   for (int s = 0; s < NS; s++)
     if (ok[s])
@@ -232,17 +247,19 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
 }
 
 // Picks the instantiation for the column's slot count (warp-uniform switch).
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int GW>
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW>
 __device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real> &a, const Real *s_told,
                                                       const Real *s_tnew, const Real *s_tnext, int4 it, int t,
                                                       Real theta_old, Real alpha, Real lam, Real mu, Real z,
-                                                      Real *s_part, int parity, int grp, int wig, int lane) {
+                                                      Real *s_part, int parity, int grp, int wig, int lane,
+                                                      Real theta_given, Real &sq, Real &lin) {
   constexpr int R = sizeof(Real) == 8 ? 4 : 8, NT = 32 * GW;
   const int n_slots = (it.z - it.y + NT - 1) / NT;
 #define MYFM_SLOTS(NS)                                                                             \
   case NS:                                                                                         \
-    return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, GW, (NS <= R ? NS : R), true>(                       \
-        a, s_told, s_tnew, s_tnext, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane);
+    return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, GW, (NS <= R ? NS : R), true>(                 \
+        a, s_told, s_tnew, s_tnext, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane,           \
+        theta_given, sq, lin);
   switch (n_slots) {
     MYFM_SLOTS(1)
     MYFM_SLOTS(2)
@@ -254,15 +271,24 @@ __device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real
     MYFM_SLOTS(8)
   }
 #undef MYFM_SLOTS
-  // empty column (one warp): the draw comes from the prior alone
-  return column_draw<Real, IS_V>(Real(0), Real(0), theta_old, alpha, lam, mu, z);
+  // no local rows (an empty column, or a column whose rows live on other ranks)
+  sq = 0, lin = 0;
+  if (MODE == FIELD_STATS)
+    return theta_old;
+  return MODE == FIELD_UPDATE ? theta_given : column_draw<Real, IS_V>(Real(0), Real(0), theta_old, alpha, lam, mu, z);
 }
 
-template <typename Real>
-__device__ __forceinline__ void field_store_theta(const FieldStreamArgs<Real> &a, int j, Real theta_new) {
-  a.theta[j] = theta_new;
-  if (a.theta_t)
-    a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+// What the leader of a column does with the result: store the draw, or (FIELD_STATS) the statistics.
+template <typename Real, int MODE>
+__device__ __forceinline__ void field_finish_column(const FieldStreamArgs<Real> &a, int j, int slot, Real theta_new,
+                                                    Real sq, Real lin) {
+  if (MODE == FIELD_STATS) {
+    a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+  } else {
+    a.theta[j] = theta_new;
+    if (a.theta_t)
+      a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
+  }
 }
 
 // Level-0 columns by length (items are sorted longest first; R = 8 rows per thread in f32, 4 in f64):
@@ -270,7 +296,7 @@ __device__ __forceinline__ void field_store_theta(const FieldStreamArgs<Real> &a
 //   nCR  up to 32 R FIELD_WARPS rows:       the whole CTA, rows in registers
 //   nG   up to 32 R FIELD_GROUP_WARPS rows: a group of four warps, rows in registers
 //   nW   up to 32 R rows:                   one warp, rows in registers, handed out dynamically
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND>
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE>
 __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_constant__ FieldStreamArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ Real scratch[32];
@@ -285,39 +311,55 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   __syncthreads();
   const Real alpha = *a.alpha;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // draw of column (j, slot) from the statistics summed over the ranks (FIELD_UPDATE)
+  auto draw_given = [&](int slot, Real theta_old, Real lam, Real mu, Real z) {
+    return column_draw<Real, IS_V>(a.colstat[2 * slot], a.colstat[2 * slot + 1], theta_old, alpha, lam, mu, z);
+  };
 
   for (int c = blockIdx.x; c < a.nCC; c += gridDim.x) {
     const int4 it = __ldg(a.item + c);
-    const int j = it.x;
+    const int j = it.x, slot = MODE == FIELD_FUSED ? 0 : a.item_slot[c];
     const Real theta_old = a.theta[j];
     const int g = a.group[j];
     const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
-    Real sq = 0, lin = 0;
-    field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_told, s_tnew, s_tnext, it.y, it.z,
-                                                                      threadIdx.x, theta_old, theta_old, alpha, sq, lin);
-    sq = block_sum(sq, scratch);
-    lin = block_sum(lin, scratch);
-    const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
-    field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_told, s_tnew, s_tnext, it.y, it.z,
-                                                                     threadIdx.x, theta_old, theta_new, alpha, sq, lin);
+    Real sq = 0, lin = 0, theta_new = theta_old;
+    if (MODE != FIELD_UPDATE) {
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+                                                                        threadIdx.x, theta_old, theta_old, alpha, sq,
+                                                                        lin);
+      sq = block_sum(sq, scratch);
+      lin = block_sum(lin, scratch);
+    }
+    if (MODE != FIELD_STATS) {
+      theta_new = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z)
+                                       : column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+                                                                       threadIdx.x, theta_old, theta_new, alpha, sq,
+                                                                       lin);
+    }
     __syncthreads(); // every thread has read theta[j]
     if (threadIdx.x == 0)
-      field_store_theta(a, j, theta_new);
+      field_finish_column<Real, MODE>(a, j, slot, theta_new, sq, lin);
   }
 
   {
     int parity = 0;
     for (int c = blockIdx.x; c < a.nCR; c += gridDim.x, parity ^= 1) {
       const int4 it = __ldg(a.item + a.nCC + c);
-      const int j = it.x;
+      const int j = it.x, slot = MODE == FIELD_FUSED ? 0 : a.item_slot[a.nCC + c];
       const Real theta_old = a.theta[j];
       const int g = a.group[j];
       const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
       constexpr int R = sizeof(Real) == 8 ? 4 : 8;
-      const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_WARPS, R, false>(
-          a, s_told, s_tnew, s_tnext, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane);
-      if (threadIdx.x == 0) // every thread read theta[j] before the barrier of the reduction
-        field_store_theta(a, j, theta_new);
+      Real sq, lin;
+      const Real given = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z) : Real(0);
+      const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_WARPS, R, false>(
+          a, s_told, s_tnew, s_tnext, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane,
+          given, sq, lin);
+      if (MODE == FIELD_UPDATE)
+        __syncthreads(); // every thread has read theta[j] (the other modes synchronise in the reduction)
+      if (threadIdx.x == 0)
+        field_finish_column<Real, MODE>(a, j, slot, theta_new, sq, lin);
     }
   }
 
@@ -326,27 +368,33 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     const int grp = warp / FIELD_GROUP_WARPS, wig = warp % FIELD_GROUP_WARPS;
     int parity = 0;
     for (int k = blockIdx.x + gridDim.x * grp; k < a.nG; k += gridDim.x * GROUPS, parity ^= 1) {
-      const int4 it = __ldg(a.item + a.nCC + a.nCR + k);
-      const int j = it.x;
+      const int item = a.nCC + a.nCR + k;
+      const int4 it = __ldg(a.item + item);
+      const int j = it.x, slot = MODE == FIELD_FUSED ? 0 : a.item_slot[item];
       const Real theta_old = a.theta[j];
       const int g = a.group[j];
       const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
-      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_GROUP_WARPS>(
+      Real sq, lin;
+      const Real given = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z) : Real(0);
+      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_GROUP_WARPS>(
           a, s_told, s_tnew, s_tnext, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
-          lane);
+          lane, given, sq, lin);
+      if (MODE == FIELD_UPDATE) // every warp of the group has read theta[j] before it changes
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(FIELD_GROUP_WARPS * 32) : "memory");
       if (wig == 0 && lane == 0)
-        field_store_theta(a, j, theta_new);
+        field_finish_column<Real, MODE>(a, j, slot, theta_new, sq, lin);
     }
   }
 
   // One warp per column.  The first batch of FIELD_BATCH columns is static, the following ones are
   // handed out through a counter (one atomic per batch: same-address atomics retire at about one
   // per two cycles chip-wide, one per column would bound the kernel).  Lane b of the warp owns the
-  // scalars of the batch's b-th column (item, theta, z, group hypers: one chain of dependent loads
-  // per BATCH, not per column), and the rows of the whole batch are pulled into L2 up front, so a
-  // column's own loads find their lines on chip.
+  // scalars of the batch's b-th column (item, theta, z, group hypers, and in FIELD_UPDATE its draw:
+  // one chain of dependent loads per BATCH, not per column), and the rows of the whole batch are
+  // pulled into L2 up front, so a column's own loads find their lines on chip.
   const int total_warps = gridDim.x * FIELD_WARPS;
-  const int4 *items_w = a.item + a.nCC + a.nCR + a.nG;
+  const int first_w = a.nCC + a.nCR + a.nG;
+  const int4 *items_w = a.item + first_w;
   int kb = (blockIdx.x + gridDim.x * warp) * FIELD_BATCH; // longest columns spread over the SMs
   while (kb < a.nW) {
     int kb_next = 0;
@@ -354,13 +402,18 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       kb_next = total_warps * FIELD_BATCH + atomicAdd(a.sched, FIELD_BATCH);
     const int n_batch = min(FIELD_BATCH, a.nW - kb);
     int4 my_it = make_int4(0, 0, 0, 0);
-    Real my_theta = 0, my_lam = 0, my_mu = 0, my_z = 0;
+    int my_slot = 0;
+    Real my_theta = 0, my_lam = 0, my_mu = 0, my_z = 0, my_given = 0;
     if (lane < n_batch) {
       my_it = __ldg(items_w + kb + lane);
       my_theta = a.theta[my_it.x];
       my_z = a.z[my_it.x];
       const int g = a.group[my_it.x];
       my_lam = a.lambda[g], my_mu = a.mu[g];
+      if (MODE != FIELD_FUSED)
+        my_slot = a.item_slot[first_w + kb + lane];
+      if (MODE == FIELD_UPDATE)
+        my_given = draw_given(my_slot, my_theta, my_lam, my_mu, my_z);
     }
     for (int bi = 0; bi < n_batch; bi++) {
       const int lo = __shfl_sync(FULL_MASK, my_it.y, bi), n = __shfl_sync(FULL_MASK, my_it.z, bi) - lo;
@@ -379,10 +432,13 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       it.z = __shfl_sync(FULL_MASK, my_it.z, bi), it.w = 0;
       const Real theta_old = __shfl_sync(FULL_MASK, my_theta, bi), lam = __shfl_sync(FULL_MASK, my_lam, bi);
       const Real mu = __shfl_sync(FULL_MASK, my_mu, bi), z = __shfl_sync(FULL_MASK, my_z, bi);
-      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, 1>(
-          a, s_told, s_tnew, s_tnext, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane);
+      const Real given = MODE == FIELD_UPDATE ? __shfl_sync(FULL_MASK, my_given, bi) : Real(0);
+      const int slot = MODE == FIELD_FUSED ? 0 : __shfl_sync(FULL_MASK, my_slot, bi);
+      Real sq, lin;
+      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, 1>(
+          a, s_told, s_tnew, s_tnext, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin);
       if (lane == 0)
-        field_store_theta(a, it.x, theta_new);
+        field_finish_column<Real, MODE>(a, it.x, slot, theta_new, sq, lin);
     }
     kb = __shfl_sync(FULL_MASK, kb_next, 0);
   }
@@ -403,6 +459,8 @@ template <typename Real> struct FieldStatsArgs {
   const Real *z;
   const int *group;
   const Real *alpha, *lambda, *mu;
+  const int *item_slot; // row shards: column slot of every item; colstat [2 * columns of the level]
+  Real *colstat;        // (nullptr on one GPU: the kernel draws itself)
   Real *partial;   // [2 nS] chunk statistics of the long columns
   int *chunk_done; // [nS] chunks finished, per long column (at its first chunk), zero between launches
   int last_base;
@@ -410,8 +468,8 @@ template <typename Real> struct FieldStatsArgs {
 };
 
 template <typename Real, bool IS_V>
-__device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int j, Real sq, Real lin,
-                                              Real theta_old, Real alpha) {
+__device__ __forceinline__ void field_publish_draw(const FieldStatsArgs<Real> &a, int j, Real sq, Real lin,
+                                                   Real theta_old, Real alpha) {
   const int g = a.group[j];
   const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[j]);
   a.theta[j] = theta_new;
@@ -419,6 +477,28 @@ __device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int
     a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
   a.pend_told[j - a.last_base] = theta_old;
   a.pend_tnew[j - a.last_base] = theta_new;
+}
+// One GPU: draw now.  Row shards: leave the local statistics for the all-reduce (k_field_draw_last draws).
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int item, int j, Real sq, Real lin,
+                                              Real theta_old, Real alpha) {
+  if (a.colstat) {
+    const int slot = a.item_slot[item];
+    a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+  } else {
+    field_publish_draw<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
+  }
+}
+
+// Row shards, after the all-reduce: one thread per column of the last level draws from the summed
+// statistics (identically on every rank).  cols: the level's columns in slot order.
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(256) k_field_draw_last(FieldStatsArgs<Real> a, const int *__restrict__ cols, int n_cols) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_cols)
+    return;
+  const int j = cols[slot];
+  field_publish_draw<Real, IS_V>(a, j, a.colstat[2 * slot], a.colstat[2 * slot + 1], a.theta[j], *a.alpha);
 }
 
 template <typename Real, bool IS_V, bool UNIT>
@@ -472,17 +552,17 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
           for (int i = it.w; i < it.w + n_chunks; i++)
             s += __ldcg(a.partial + 2 * i), l += __ldcg(a.partial + 2 * i + 1);
           a.chunk_done[it.w] = 0;
-          field_publish<Real, IS_V>(a, j, s, l, theta_old, alpha);
+          field_publish<Real, IS_V>(a, it.w, j, s, l, theta_old, alpha);
         }
       } else {
-        field_publish<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
+        field_publish<Real, IS_V>(a, b, j, sq, lin, theta_old, alpha);
       }
     }
   } else {
     sq = warp_sum(sq);
     lin = warp_sum(lin);
     if (lane == 0)
-      field_publish<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
+      field_publish<Real, IS_V>(a, a.nS + a.nC + w, j, sq, lin, theta_old, alpha);
   }
 }
 

@@ -86,6 +86,20 @@ def _collective_device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
 
+def _fresh_unique_id(group=None) -> bytes:
+    """Collective: rank 0 draws an ncclUniqueId, every rank receives it.  One id serves ONE
+    communicator, i.e. one trainer."""
+    import torch.distributed as dist
+
+    box = [None]
+    if dist.get_rank(group) == 0:
+        buf = (C.c_char * 128)()
+        _lib.check(_lib.lib().myfm_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        box[0] = bytes(buf.raw)
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
 @dataclass
 class ShardContext:
     world_size: int
@@ -94,12 +108,21 @@ class ShardContext:
     n_rows_global: int
     nccl_unique_id: Optional[bytes]
     column_level: np.ndarray
+    group: object = None
+    _id_used: bool = False
 
     @contextlib.contextmanager
     def options(self, **kwargs) -> Iterator[None]:
-        """engine_options(...) carrying this shard's description."""
+        """engine_options(...) carrying this shard's description.  Collective when NCCL is in use:
+        every trainer needs its own communicator, so every use after the first fetches a fresh
+        ncclUniqueId from rank 0 (create one trainer per `with` block)."""
+        uid = self.nccl_unique_id
+        if uid is not None:
+            if self._id_used:
+                uid = _fresh_unique_id(self.group)
+            self._id_used = True
         with engine_options(world_size=self.world_size, rank=self.rank, row_offset=self.row_offset,
-                            n_rows_global=self.n_rows_global, nccl_unique_id=self.nccl_unique_id,
+                            n_rows_global=self.n_rows_global, nccl_unique_id=uid,
                             column_level=self.column_level, **kwargs):
             yield
 
@@ -110,16 +133,8 @@ def context(X_local, row_offset: int, n_rows_global: int, group=None, with_nccl:
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     levels = agree_on_levels(X_local, group)
-    uid = None
-    if with_nccl and world > 1:
-        box = [None]
-        if rank == 0:
-            buf = (C.c_char * 128)()
-            _lib.check(_lib.lib().myfm_nccl_unique_id(C.cast(buf, C.c_void_p)))
-            box[0] = bytes(buf.raw)
-        dist.broadcast_object_list(box, src=0, group=group)
-        uid = box[0]
-    return ShardContext(world, rank, int(row_offset), int(n_rows_global), uid, levels)
+    uid = _fresh_unique_id(group) if with_nccl and world > 1 else None
+    return ShardContext(world, rank, int(row_offset), int(n_rows_global), uid, levels, group)
 
 
 def shard(X, y, group=None, with_nccl: bool = True):
