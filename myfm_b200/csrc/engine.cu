@@ -37,6 +37,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 
   static NcclApi &get() {
@@ -62,6 +63,7 @@ struct NcclApi {
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
     return a;
   }
@@ -426,6 +428,13 @@ template <typename Real> struct Trainer : TrainerBase {
   DevBuf<SweepItem> f_items0, f_itemsL;
   DevBuf<int> f_seg_countL, f_tail_idx, f_sched, f_chunk_done, f_item_slot0, f_item_slotL, f_colsL;
   DevBuf<Real> f_colstat; // row shards: column statistics of a level, summed over the ranks
+  // peer-memory exchange of those statistics (field_sweep.cuh: PeerView); falls back to NCCL
+  bool peer_ok = false;
+  int my_rank = 0;
+  unsigned char *peer_local = nullptr;       // this rank's buffer: header, statistics buffer 0 and 1
+  std::vector<unsigned char *> peer_base;    // every rank's buffer as mapped here (own: peer_local)
+  size_t peer_stat_elems = 0;                // Reals per statistics buffer
+  unsigned long long peer_seq = 0;           // collectives issued so far
   int f_ncols0 = 0, f_ncolsL = 0;
   DevBuf<Real> f_tail_val, f_own_val, f_pend_told, f_pend_tnew, f_partial;
 
@@ -688,6 +697,9 @@ template <typename Real> struct Trainer : TrainerBase {
       flag.download(&all, 1, stream);
       MYFM_CUDA(cudaStreamSynchronize(stream));
       field_path = all != 0;
+      my_rank = o.rank;
+      if (field_path)
+        setup_peer_exchange();
     }
     // Gamma shapes are data independent (FMTrainer.hpp:140,157)
     shape_alpha = (static_cast<Real>(cfg.alpha_0) + N_global) / 2;
@@ -704,6 +716,13 @@ template <typename Real> struct Trainer : TrainerBase {
     reset_graphs();
     if (rng_stream)
       cudaStreamSynchronize(rng_stream);
+    if (peer_ok && comm) { // no rank unmaps its buffer while a peer's last kernel may still read it
+      NcclApi &nccl = NcclApi::get();
+      if (peer_error.p && nccl.AllReduce(peer_error.p, peer_error.p, 1, ncclInt, ncclMax, comm, stream) == ncclSuccess)
+        cudaStreamSynchronize(stream);
+    }
+    if (!peer_base.empty() || peer_local)
+      close_peer_exchange();
     if (comm)
       NcclApi::get().CommDestroy(comm);
     for (auto *evs : {z_copied, z_ready, z_free})
@@ -912,6 +931,13 @@ template <typename Real> struct Trainer : TrainerBase {
   }
 
   void check_rng_error() {
+    if (peer_ok) {
+      int perr = 0;
+      MYFM_CUDA(cudaMemcpyAsync(&perr, peer_error.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+      if (perr)
+        throw std::runtime_error("row-sharded training: a peer rank never published its column statistics.");
+    }
     if (!device_rng)
       return;
     int err = 0;
@@ -1128,6 +1154,99 @@ template <typename Real> struct Trainer : TrainerBase {
     field_path = true;
   }
 
+  // Maps every rank's statistics buffer into this process (cudaIpc over the NVLink / NVSwitch
+  // fabric of one node).  Collective; any failure on any rank leaves every rank on NCCL.
+  void setup_peer_exchange() {
+    peer_ok = false;
+    const char *off = std::getenv("MYFM_NO_PEER");
+    NcclApi &nccl = NcclApi::get();
+    int ok = !(off && off[0] == '1') && world <= PEER_MAX_RANKS;
+    peer_stat_elems = 2 * static_cast<size_t>(std::max(f_ncols0, f_ncolsL));
+    const size_t bytes = PEER_HEADER_BYTES + 2 * peer_stat_elems * sizeof(Real);
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok) {
+      if (cudaMalloc(&peer_local, bytes) != cudaSuccess || cudaMemset(peer_local, 0, bytes) != cudaSuccess ||
+          cudaIpcGetMemHandle(&mine, peer_local) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+      }
+    }
+    // handles of all ranks, and whether every rank got this far
+    DevBuf<unsigned char> send(sizeof(mine) + 4), recv((sizeof(mine) + 4) * static_cast<size_t>(world));
+    std::vector<unsigned char> h(sizeof(mine) + 4);
+    std::memcpy(h.data(), &mine, sizeof(mine));
+    std::memcpy(h.data() + sizeof(mine), &ok, 4);
+    send.upload(h, stream);
+    nccl.check(nccl.AllGather(send.p, recv.p, h.size(), ncclChar, comm, stream), "ncclAllGather");
+    std::vector<unsigned char> all(h.size() * world);
+    recv.download(all.data(), all.size(), stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    for (int r = 0; r < world; r++) {
+      int theirs = 0;
+      std::memcpy(&theirs, all.data() + r * h.size() + sizeof(mine), 4);
+      ok = ok && theirs;
+    }
+    peer_base.assign(world, nullptr);
+    if (ok) {
+      for (int r = 0; r < world && ok; r++) {
+        if (r == my_rank) {
+          peer_base[r] = peer_local;
+          continue;
+        }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, all.data() + r * h.size(), sizeof(hd));
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+        }
+        peer_base[r] = static_cast<unsigned char *>(p);
+      }
+    }
+    // second agreement: every mapping succeeded everywhere
+    DevBuf<int> flag(1);
+    flag.upload(&ok, 1, stream);
+    nccl.check(nccl.AllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, comm, stream), "ncclAllReduce");
+    flag.download(&ok, 1, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    peer_ok = ok != 0;
+    peer_seq = 0;
+    peer_error.alloc(1);
+    peer_error.zero(stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    if (!peer_ok)
+      close_peer_exchange();
+  }
+  void close_peer_exchange() {
+    for (int r = 0; r < static_cast<int>(peer_base.size()); r++)
+      if (peer_base[r] && r != my_rank)
+        cudaIpcCloseMemHandle(peer_base[r]);
+    peer_base.clear();
+    if (peer_local)
+      cudaFree(peer_local);
+    peer_local = nullptr;
+    peer_ok = false;
+  }
+  Real *peer_stat(int r, unsigned long long seq) const {
+    return reinterpret_cast<Real *>(peer_base[r] + PEER_HEADER_BYTES) + (seq & 1) * peer_stat_elems;
+  }
+  // Starts collective peer_seq + 1: where this rank's partial statistics go.
+  Real *peer_begin() { return peer_stat(my_rank, ++peer_seq); }
+  // Publishes them (after the producing kernel, in stream order) and describes the collective to the consumer.
+  PeerView<Real> peer_publish() {
+    k_peer_post<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long *>(peer_local), peer_seq);
+    launched();
+    PeerView<Real> pv;
+    pv.world = world, pv.seq = peer_seq, pv.error = peer_error.p;
+    for (int r = 0; r < world; r++) {
+      pv.stat[r] = peer_stat(r, peer_seq);
+      pv.posted[r] = reinterpret_cast<const unsigned long long *>(peer_base[r]);
+    }
+    return pv;
+  }
+  DevBuf<int> peer_error;
+
   template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a, int mode) {
     if (IS_V && f_tail > 1)
       launch_field_stream_mid<IS_V, UNIT, true, PEND>(a, mode);
@@ -1182,10 +1301,14 @@ template <typename Real> struct Trainer : TrainerBase {
     launch_field_stream<V, true, P>(a, mode);                                                      \
   else                                                                                             \
     launch_field_stream<V, false, P>(a, mode);
-      // one GPU: one fused pass.  Row shards: statistics, all-reduce over the ranks, update.
+      // one GPU: one fused pass.  Row shards: statistics, sum over the ranks (peer memory inside the
+      // update kernel, or an NCCL all-reduce between the two), update.
+      a.peer.world = 0;
       for (int pass = 0; pass < (world > 1 ? 2 : 1); pass++) {
         const int mode = world > 1 ? (pass == 0 ? FIELD_STATS : FIELD_UPDATE) : FIELD_FUSED;
         a.sched = f_sched.p + (f_launch++);
+        if (mode == FIELD_STATS && peer_ok)
+          a.colstat = peer_begin();
         if (!IS_V) {
           if (pend != PEND_NONE)
             throw std::logic_error("field path: the w sweep must not find a pending update.");
@@ -1197,8 +1320,12 @@ template <typename Real> struct Trainer : TrainerBase {
         } else {
           MYFM_FS(true, PEND_V)
         }
-        if (mode == FIELD_STATS)
-          allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncols0));
+        if (mode == FIELD_STATS) {
+          if (peer_ok)
+            a.peer = peer_publish();
+          else
+            allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncols0));
+        }
       }
 #undef MYFM_FS
     }
@@ -1215,7 +1342,8 @@ template <typename Real> struct Trainer : TrainerBase {
       a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
       a.partial = f_partial.p, a.chunk_done = f_chunk_done.p, a.last_base = f_last_base;
-      a.item_slot = f_item_slotL.p + f_levelL.s0, a.colstat = world > 1 ? f_colstat.p : nullptr;
+      a.item_slot = f_item_slotL.p + f_levelL.s0;
+      a.colstat = world > 1 ? (peer_ok ? peer_begin() : f_colstat.p) : nullptr;
       a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
       const int grid = a.nS + a.nC + ceil_div(a.nW, STATS_THREADS / 32);
       if (grid) {
@@ -1226,8 +1354,13 @@ template <typename Real> struct Trainer : TrainerBase {
         launched();
       }
       if (world > 1) { // statistics of this rank's rows -> sum over the ranks -> identical draw everywhere
-        allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncolsL));
-        k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, f_colsL.p, f_ncolsL);
+        PeerView<Real> pv;
+        pv.world = 0;
+        if (peer_ok)
+          pv = peer_publish();
+        else
+          allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncolsL));
+        k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, pv, f_colsL.p, f_ncolsL);
         launched();
       }
     }
@@ -1805,7 +1938,7 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
   int64_t launch_count() const override { return launches; }
-  int sweep_path() const override { return field_path ? 1 : 0; }
+  int sweep_path() const override { return field_path ? (peer_ok ? 2 : 1) : 0; }
   std::unique_ptr<SampleBase> snapshot() override { // device-to-device copy of the current sample
     require_fm();
     MYFM_CUDA(cudaSetDevice(device));

@@ -38,6 +38,58 @@ enum { PEND_NONE = 0, PEND_W = 1, PEND_V = 2 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ------------------------------------------------------------------------------------------------
+// Row shards on one NVLink / NVSwitch node: the all-reduce of the column statistics is fused into
+// the kernels through peer memory instead of being a collective of its own.  Every rank owns a
+// buffer that all peers map (cudaIpc): a header with the sequence number of the last collective
+// whose local statistics are complete, then two statistics buffers used alternately.  The
+// producing kernel writes this rank's partial sums into its own buffer, k_peer_post publishes the
+// sequence number, and the consuming kernel — after seeing the sequence number on every peer —
+// reads the partial sums of ALL ranks straight over NVLink and adds them in rank order, so every
+// rank forms bit-identical sums.  A rank cannot run two collectives ahead of a peer (it needs the
+// peer's sequence number first), which makes two buffers enough.
+// ------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_HEADER_BYTES = 256;
+template <typename Real> struct PeerView {
+  int world = 0;                 // 0: not in use (one GPU, or NCCL all-reduce between the passes)
+  unsigned long long seq = 0;    // the collective this launch consumes
+  const Real *stat[PEER_MAX_RANKS];                 // every rank's statistics buffer of this collective
+  const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's sequence number
+  int *error;                    // set when a peer never shows up
+};
+
+__global__ void k_peer_post(unsigned long long *posted, unsigned long long seq) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(posted) = seq;
+}
+
+// Block-wide: returns once every rank has published `seq` (bounded: a dead peer raises the error flag).
+template <typename Real> __device__ __forceinline__ void peer_wait(const PeerView<Real> &pv) {
+  if (pv.world == 0)
+    return;
+  if (threadIdx.x < pv.world) {
+    const volatile unsigned long long *flag = pv.posted[threadIdx.x];
+    long long spins = 0;
+    while (*flag < pv.seq) {
+      if (++spins > (1ll << 23)) { // a few seconds of polling over NVLink
+        *pv.error = 3;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+// (sq, lin) of column `slot` summed over the ranks in rank order.
+template <typename Real> __device__ __forceinline__ void peer_sum(const PeerView<Real> &pv, int slot, Real &sq, Real &lin) {
+  sq = 0, lin = 0;
+  for (int r = 0; r < pv.world; r++) {
+    sq += __ldcv(pv.stat[r] + 2 * slot);
+    lin += __ldcv(pv.stat[r] + 2 * slot + 1);
+  }
+}
+
 template <typename Real> struct FieldStreamArgs {
   const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
   int nCC, nCR, nG, nW;
@@ -62,6 +114,7 @@ template <typename Real> struct FieldStreamArgs {
   // over the ranks between the two passes
   const int *item_slot; // column slot of every item (same numbering on every rank)
   Real *colstat;        // [2 * columns of level 0]
+  PeerView<Real> peer;  // FIELD_UPDATE: where the summed statistics come from (world == 0: colstat)
 };
 
 // One GPU: FIELD_FUSED (statistics, draw and update in one pass).  Row shards: the rows of a column
@@ -313,8 +366,15 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // draw of column (j, slot) from the statistics summed over the ranks (FIELD_UPDATE)
   auto draw_given = [&](int slot, Real theta_old, Real lam, Real mu, Real z) {
-    return column_draw<Real, IS_V>(a.colstat[2 * slot], a.colstat[2 * slot + 1], theta_old, alpha, lam, mu, z);
+    Real sq, lin;
+    if (a.peer.world)
+      peer_sum(a.peer, slot, sq, lin);
+    else
+      sq = a.colstat[2 * slot], lin = a.colstat[2 * slot + 1];
+    return column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
   };
+  if (MODE == FIELD_UPDATE)
+    peer_wait(a.peer);
 
   for (int c = blockIdx.x; c < a.nCC; c += gridDim.x) {
     const int4 it = __ldg(a.item + c);
@@ -331,8 +391,13 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       lin = block_sum(lin, scratch);
     }
     if (MODE != FIELD_STATS) {
-      theta_new = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z)
-                                       : column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+      if (MODE == FIELD_UPDATE) {
+        if (lane == 0)
+          theta_new = draw_given(slot, theta_old, lam, mu, z);
+        theta_new = __shfl_sync(FULL_MASK, theta_new, 0);
+      } else {
+        theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+      }
       field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_told, s_tnew, s_tnext, it.y, it.z,
                                                                        threadIdx.x, theta_old, theta_new, alpha, sq,
                                                                        lin);
@@ -352,7 +417,12 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
       constexpr int R = sizeof(Real) == 8 ? 4 : 8;
       Real sq, lin;
-      const Real given = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z) : Real(0);
+      Real given = 0;
+      if (MODE == FIELD_UPDATE) { // one lane per warp reads the (possibly remote) statistics
+        if (lane == 0)
+          given = draw_given(slot, theta_old, lam, mu, z);
+        given = __shfl_sync(FULL_MASK, given, 0);
+      }
       const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_WARPS, R, false>(
           a, s_told, s_tnew, s_tnext, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane,
           given, sq, lin);
@@ -375,7 +445,12 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       const int g = a.group[j];
       const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
       Real sq, lin;
-      const Real given = MODE == FIELD_UPDATE ? draw_given(slot, theta_old, lam, mu, z) : Real(0);
+      Real given = 0;
+      if (MODE == FIELD_UPDATE) {
+        if (lane == 0)
+          given = draw_given(slot, theta_old, lam, mu, z);
+        given = __shfl_sync(FULL_MASK, given, 0);
+      }
       const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_GROUP_WARPS>(
           a, s_told, s_tnew, s_tnext, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
           lane, given, sq, lin);
@@ -493,12 +568,19 @@ __device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int
 // Row shards, after the all-reduce: one thread per column of the last level draws from the summed
 // statistics (identically on every rank).  cols: the level's columns in slot order.
 template <typename Real, bool IS_V>
-__global__ void __launch_bounds__(256) k_field_draw_last(FieldStatsArgs<Real> a, const int *__restrict__ cols, int n_cols) {
+__global__ void __launch_bounds__(256)
+    k_field_draw_last(FieldStatsArgs<Real> a, PeerView<Real> peer, const int *__restrict__ cols, int n_cols) {
+  peer_wait(peer);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_cols)
     return;
   const int j = cols[slot];
-  field_publish_draw<Real, IS_V>(a, j, a.colstat[2 * slot], a.colstat[2 * slot + 1], a.theta[j], *a.alpha);
+  Real sq, lin;
+  if (peer.world)
+    peer_sum(peer, slot, sq, lin);
+  else
+    sq = a.colstat[2 * slot], lin = a.colstat[2 * slot + 1];
+  field_publish_draw<Real, IS_V>(a, j, sq, lin, a.theta[j], *a.alpha);
 }
 
 template <typename Real, bool IS_V, bool UNIT>

@@ -38,9 +38,12 @@ def _state(trainer):
     return np.concatenate([[w0], w, V.ravel(), [h.alpha], h.mu_w, h.lambda_w, h.mu_V.ravel(), h.lambda_V.ravel()])
 
 
-def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir: str) -> None:
+def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir: str, exchange: str,
+            no_field: bool) -> None:
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ["MYFM_NO_PEER"] = "0" if exchange == "peer" else "1"
+    os.environ["MYFM_NO_FIELD_PATH"] = "1" if no_field else "0"
     import torch
     import torch.distributed as dist
 
@@ -56,6 +59,8 @@ def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir
         with ctx.options(dtype=dtype, device=rank):
             t = _TrainerHandle(X_local, [], y_local, 42, _config(group_shapes, n_sweeps))
             t.init_fm(6, 0.1)
+        # 0 general level kernels, 1 field path + NCCL all-reduce, 2 field path + peer-memory exchange
+        assert t.sweep_path() == (0 if no_field else (2 if exchange == "peer" else 1)), t.sweep_path()
         states = []
         for _ in range(n_sweeps):
             t.step(1)
@@ -67,8 +72,12 @@ def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_two_gpus_match_one(engine, dtype, tmp_path):
+@pytest.mark.parametrize("dtype,exchange,no_field", [("f64", "peer", False), ("f32", "peer", False),
+                                                    ("f64", "nccl", False), ("f64", "nccl", True)])
+def test_two_gpus_match_one(engine, dtype, exchange, no_field, tmp_path):
+    """2 row shards == 1 GPU on the whole data (f64 1e-8), replicas bit-identical, for the three
+    row-sharded schedules: field path with the statistics exchanged through peer memory, field
+    path with NCCL all-reduces, general level kernels with NCCL all-reduces."""
     from myfm_b200 import _lib
 
     if _lib.device_count() < 2:
@@ -78,7 +87,7 @@ def test_two_gpus_match_one(engine, dtype, tmp_path):
     from myfm_b200._myfm import _TrainerHandle
 
     n_sweeps = 4
-    mp.spawn(_worker, args=(2, _free_port(), dtype, n_sweeps, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), dtype, n_sweeps, str(tmp_path), exchange, no_field), nprocs=2, join=True)
     X, y, group_shapes = _data()
     with engine.engine_options(dtype=dtype):
         t = _TrainerHandle(X, [], y, 42, _config(group_shapes, n_sweeps))
