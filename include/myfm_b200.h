@@ -163,7 +163,8 @@ int myfm_trainer_get_variates(myfm_trainer_t *t, double *out, int64_t capacity, 
 int myfm_trainer_mh_accept(myfm_trainer_t *t, int32_t g, int64_t *count);
 /* which schedule the main-table column sweeps use: 0 = general dependency-level kernels,
  * 1 = field path (streaming level 0 + gather-only last level, csrc/field_sweep.cuh), 2 = field path
- * on row shards with the column statistics exchanged through peer memory (NVLink).  All are the
+ * on row shards with the column statistics exchanged through peer memory (NVLink); 3 / 4 = 1 / 2
+ * with rank-exclusive level-0 columns (no exchange for the streaming level).  All are the
  * reference's update_w / update_V (FMTrainer.hpp:231-486); diagnostics and tests only. */
 int myfm_trainer_sweep_path(const myfm_trainer_t *t, int32_t *path);
 /* number of kernels this trainer has launched so far (bench.py's gpu_launches) */

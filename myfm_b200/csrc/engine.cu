@@ -428,6 +428,13 @@ template <typename Real> struct Trainer : TrainerBase {
   DevBuf<SweepItem> f_items0, f_itemsL;
   DevBuf<int> f_seg_countL, f_tail_idx, f_sched, f_chunk_done, f_item_slot0, f_item_slotL, f_colsL;
   DevBuf<Real> f_colstat; // row shards: column statistics of a level, summed over the ranks
+  // Row shards whose level-0 columns are rank-exclusive (every such column has all its rows on one
+  // rank, e.g. rows partitioned by user): level 0 needs no exchange at all — each rank sweeps the
+  // columns it owns in the fused single pass, and the owners' draws are merged once per sweep.
+  bool f_exclusive = false;
+  std::vector<SweepItem> f_items0_host;
+  std::vector<int> f_slot0_host, f_level_host;
+  DevBuf<int> f_owner; // [dim_all] rank that holds the authoritative copy of w[j], V[j, :]
   // peer-memory exchange of those statistics (field_sweep.cuh: PeerView); falls back to NCCL
   bool peer_ok = false;
   int my_rank = 0;
@@ -698,8 +705,10 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaStreamSynchronize(stream));
       field_path = all != 0;
       my_rank = o.rank;
-      if (field_path)
+      if (field_path) {
+        setup_exclusive_level0();
         setup_peer_exchange();
+      }
     }
     // Gamma shapes are data independent (FMTrainer.hpp:140,157)
     shape_alpha = (static_cast<Real>(cfg.alpha_0) + N_global) / 2;
@@ -1110,6 +1119,8 @@ template <typename Real> struct Trainer : TrainerBase {
       else
         f_nW++;
     }
+    f_items0_host = p0.items, f_slot0_host = p0.item_slot;
+    f_level_host = level;
     f_items0.upload(p0.items, stream);
     f_itemsL.upload(pL.items, stream);
     f_seg_countL.upload(pL.seg_count, stream);
@@ -1152,6 +1163,78 @@ template <typename Real> struct Trainer : TrainerBase {
     f_pend_tnew.zero(stream);
     MYFM_CUDA(cudaStreamSynchronize(stream)); // host staging vectors die here
     field_path = true;
+  }
+
+  // Collective: decides whether every level-0 column lives on one rank only and, if so, restricts
+  // this rank's level-0 work items to the columns it owns (columns without rows anywhere are dealt
+  // round-robin).
+  void setup_exclusive_level0() {
+    f_exclusive = false;
+    const char *off = std::getenv("MYFM_NO_EXCLUSIVE");
+    NcclApi &nccl = NcclApi::get();
+    const size_t n0 = f_items0_host.size();
+    // per level-0 column slot: (1 << 16 | rank + 1) when this rank holds rows of it
+    std::vector<int> mine(std::max<size_t>(1, n0), 0);
+    for (size_t k = 0; k < n0; k++)
+      if (f_items0_host[k].hi > f_items0_host[k].lo)
+        mine[f_slot0_host[k]] = (1 << 16) | (my_rank + 1);
+    if (off && off[0] == '1')
+      mine[0] = (2 << 16); // vetoes the mode on every rank
+    DevBuf<int> buf(mine.size());
+    buf.upload(mine, stream);
+    nccl.check(nccl.AllReduce(buf.p, buf.p, mine.size(), ncclInt, ncclSum, comm, stream), "ncclAllReduce");
+    std::vector<int> all(mine.size());
+    buf.download(all.data(), all.size(), stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    for (size_t sl = 0; sl < n0; sl++)
+      if ((all[sl] >> 16) > 1)
+        return; // some column is split between ranks: the two-pass schedule handles that
+    std::vector<int> owner(std::max<int64_t>(1, D_all_main()), 0); // everything else: rank 0's copy counts
+    std::vector<SweepItem> kept;
+    const int rows_per_warp = 32 * (sizeof(Real) == 8 ? 4 : 8);
+    f_nCC = f_nCR = f_nG = f_nW = 0;
+    for (size_t k = 0; k < n0; k++) { // items are sorted longest first: filtering keeps the class order
+      const int sl = f_slot0_host[k];
+      const int who = (all[sl] >> 16) ? (all[sl] & 0xffff) - 1 : sl % world;
+      owner[f_items0_host[k].col] = who;
+      if (who != my_rank)
+        continue;
+      kept.push_back(f_items0_host[k]);
+      const int len = f_items0_host[k].hi - f_items0_host[k].lo;
+      if (len > rows_per_warp * FIELD_WARPS)
+        f_nCC++;
+      else if (len > rows_per_warp * FIELD_GROUP_WARPS)
+        f_nCR++;
+      else if (len > rows_per_warp)
+        f_nG++;
+      else
+        f_nW++;
+    }
+    if (kept.empty())
+      kept.push_back(SweepItem{0, 0, 0, 0}); // never read (all counts are zero)
+    f_items0.upload(kept, stream);
+    owner.resize(std::max<int64_t>(1, D_all), 0);
+    f_owner.upload(owner, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    f_exclusive = true;
+  }
+  int64_t D_all_main() const { return static_cast<int64_t>(f_level_host.size()); }
+
+  // Exclusive level 0, end of the column sweeps: every rank keeps only the entries it owns, the sum
+  // over the ranks (zeros elsewhere: exact) is the complete, identical sample on every rank.
+  void merge_owned() {
+    if (!f_exclusive)
+      return;
+    const int64_t n_v = D_all * static_cast<int64_t>(K);
+    k_mask_owned<Real><<<ceil_div(D_all, 256), 256, 0, stream>>>(D_all, 1, f_owner.p, my_rank, w.p);
+    allreduce_sum(w.p, D_all);
+    launched();
+    if (n_v) {
+      k_mask_owned<Real><<<ceil_div(n_v, 256), 256, 0, stream>>>(D_all, K, f_owner.p, my_rank, V.p);
+      allreduce_sum(V.p, n_v);
+      k_transpose_V<Real><<<ceil_div(n_v, 256), 256, 0, stream>>>(D_all, K, V.p, Vt.p);
+      launched(2);
+    }
   }
 
   // Maps every rank's statistics buffer into this process (cudaIpc over the NVLink / NVSwitch
@@ -1304,8 +1387,9 @@ template <typename Real> struct Trainer : TrainerBase {
       // one GPU: one fused pass.  Row shards: statistics, sum over the ranks (peer memory inside the
       // update kernel, or an NCCL all-reduce between the two), update.
       a.peer.world = 0;
-      for (int pass = 0; pass < (world > 1 ? 2 : 1); pass++) {
-        const int mode = world > 1 ? (pass == 0 ? FIELD_STATS : FIELD_UPDATE) : FIELD_FUSED;
+      const bool two_pass = world > 1 && !f_exclusive;
+      for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
+        const int mode = two_pass ? (pass == 0 ? FIELD_STATS : FIELD_UPDATE) : FIELD_FUSED;
         a.sched = f_sched.p + (f_launch++);
         if (mode == FIELD_STATS && peer_ok)
           a.colstat = peer_begin();
@@ -1708,6 +1792,7 @@ template <typename Real> struct Trainer : TrainerBase {
       launched();
     }
     update_V(z + L.z_V);
+    merge_owned();
     f_pending_valid = false; // update_e overwrites e: the last vector's pending update is dropped
     { // update_e
       TimedSpan span(timer, stream, 2);
@@ -1938,7 +2023,7 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
   int64_t launch_count() const override { return launches; }
-  int sweep_path() const override { return field_path ? (peer_ok ? 2 : 1) : 0; }
+  int sweep_path() const override { return field_path ? (peer_ok ? 2 : 1) + (f_exclusive ? 2 : 0) : 0; }
   std::unique_ptr<SampleBase> snapshot() override { // device-to-device copy of the current sample
     require_fm();
     MYFM_CUDA(cudaSetDevice(device));

@@ -1041,6 +1041,16 @@ __global__ void __launch_bounds__(256)
   out[static_cast<size_t>(i) * (n_cpt + 1) + n_cpt] += 1 - prev;
 }
 
+// theta[j + D * r] = 0 unless this rank owns feature j (row shards with rank-exclusive level-0
+// columns: the sum over the ranks then rebuilds the complete vector exactly)
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_mask_owned(int64_t D, int K, const int *__restrict__ owner, int my_rank, Real *__restrict__ theta) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t < D * K && owner[t % D] != my_rank)
+    theta[t] = 0;
+}
+
 // widening copy for the getters (the boundary speaks float64)
 template <typename Real>
 __global__ void __launch_bounds__(256) k_to_double(int64_t n, const Real *__restrict__ in, double *__restrict__ out) {

@@ -110,6 +110,7 @@ class ShardContext:
     column_level: np.ndarray
     group: object = None
     _id_used: bool = False
+    rows: Optional[np.ndarray] = None  # global indices of this rank's rows (set by shard())
 
     @contextlib.contextmanager
     def options(self, **kwargs) -> Iterator[None]:
@@ -137,11 +138,42 @@ def context(X_local, row_offset: int, n_rows_global: int, group=None, with_nccl:
     return ShardContext(world, rank, int(row_offset), int(n_rows_global), uid, levels, group)
 
 
-def shard(X, y, group=None, with_nccl: bool = True):
-    """Takes this rank's contiguous row range of a dataset every rank holds in full."""
+def column_partition(X: sps.csr_matrix, world_size: int) -> np.ndarray:
+    """Rank of every row when rows are dealt out by their FIRST column (for one-hot / categorical
+    tables: by the category of the first field, e.g. by user), contiguous column ranges balanced by
+    row count.  Every first-field column then has all its rows on one rank, which lets the engine
+    sweep that field without any exchange between the GPUs."""
+    n = X.shape[0]
+    key = np.full(n, -1, dtype=np.int64)
+    has = np.diff(X.indptr) > 0
+    key[has] = X.indices[X.indptr[:-1][has]]
+    counts = np.bincount(key + 1, minlength=X.shape[1] + 1)  # slot 0: rows without entries
+    upto = np.cumsum(counts)                                  # rows with key <= k
+    # column k goes to the rank in which the middle of its block of rows falls
+    mid = upto - counts / 2.0
+    rank_of_key = np.minimum((mid * world_size / max(1, n)).astype(np.int64), world_size - 1)
+    return rank_of_key[key + 1]
+
+
+def shard(X, y, group=None, with_nccl: bool = True, partition: str = "column"):
+    """Takes this rank's rows of a dataset every rank holds in full.
+
+    partition="column" (default): rows are dealt out by their first column (`column_partition`);
+    partition="rows": contiguous row ranges (`shard_bounds`).  Either way the engine sums the
+    per-column statistics over the ranks wherever a column's rows are spread over several of them."""
     import torch.distributed as dist
 
     X = sps.csr_matrix(X)
-    lo, hi = shard_bounds(X.shape[0], dist.get_world_size(group), dist.get_rank(group))
-    X_local, y_local = X[lo:hi], np.asarray(y)[lo:hi]
-    return X_local, y_local, context(X_local, lo, X.shape[0], group, with_nccl)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if partition == "rows":
+        lo, hi = shard_bounds(X.shape[0], world, rank)
+        rows = np.arange(lo, hi)
+    elif partition == "column":
+        X.sort_indices()
+        rows = np.flatnonzero(column_partition(X, world) == rank)
+    else:
+        raise ValueError("partition must be 'column' or 'rows'")
+    X_local, y_local = X[rows], np.asarray(y)[rows]
+    ctx = context(X_local, int(rows[0]) if rows.size else 0, X.shape[0], group, with_nccl)
+    ctx.rows = rows
+    return X_local, y_local, ctx

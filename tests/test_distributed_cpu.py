@@ -18,7 +18,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, case: str, out_dir: str) -> None:
+def _worker(rank: int, world: int, port: int, case: str, out_dir: str, partition: str) -> None:
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -29,10 +29,10 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str) -> None:
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         X = _case(case)
-        X_local, _, ctx = mdist.shard(X, np.zeros(X.shape[0]), with_nccl=False)
+        X_local, _, ctx = mdist.shard(X, np.zeros(X.shape[0]), with_nccl=False, partition=partition)
         assert ctx.world_size == world and ctx.rank == rank and ctx.n_rows_global == X.shape[0]
         np.save(os.path.join(out_dir, f"levels_{rank}.npy"), ctx.column_level)
-        np.save(os.path.join(out_dir, f"bounds_{rank}.npy"), np.asarray([ctx.row_offset, ctx.row_offset + X_local.shape[0]]))
+        np.save(os.path.join(out_dir, f"rows_{rank}.npy"), ctx.rows)
     finally:
         dist.destroy_process_group()
 
@@ -60,22 +60,30 @@ def _case(case: str) -> sps.csr_matrix:
     return sps.random(400, 60, density=0.05, random_state=np.random.RandomState(5), format="csr")
 
 
+@pytest.mark.parametrize("partition", ["rows", "column"])
 @pytest.mark.parametrize("case", ["onehot", "chain", "random"])
-def test_level_consensus_two_ranks(case, tmp_path):
+def test_level_consensus_two_ranks(case, partition, tmp_path):
     import torch.multiprocessing as mp
 
     sys.path.insert(0, ROOT)
     from myfm_b200 import distributed as mdist
 
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, case, str(tmp_path), partition), nprocs=world, join=True)
     X = _case(case)
     want = mdist.local_levels(X)  # one process, whole matrix
     got = [np.load(tmp_path / f"levels_{r}.npy") for r in range(world)]
     np.testing.assert_array_equal(got[0], got[1])
     np.testing.assert_array_equal(got[0], want)
-    bounds = [np.load(tmp_path / f"bounds_{r}.npy") for r in range(world)]
-    assert bounds[0][0] == 0 and bounds[0][1] == bounds[1][0] and bounds[1][1] == X.shape[0]
+    rows = [np.load(tmp_path / f"rows_{r}.npy") for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(X.shape[0]))  # a partition of the rows
+    if partition == "rows":
+        assert rows[0][0] == 0 and rows[0][-1] + 1 == rows[1][0] and rows[1][-1] + 1 == X.shape[0]
+    else:  # every first column has all its rows on one rank
+        Xs = sps.csr_matrix(X)
+        Xs.sort_indices()
+        first = [set(Xs.indices[Xs.indptr[r]] for r in rr if Xs.indptr[r + 1] > Xs.indptr[r]) for rr in rows]
+        assert not (first[0] & first[1])
 
 
 def test_shard_bounds_cover_all_rows():

@@ -39,7 +39,7 @@ def _state(trainer):
 
 
 def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir: str, exchange: str,
-            no_field: bool) -> None:
+            no_field: bool, partition: str) -> None:
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     os.environ["MYFM_NO_PEER"] = "0" if exchange == "peer" else "1"
@@ -55,29 +55,35 @@ def _worker(rank: int, world: int, port: int, dtype: str, n_sweeps: int, out_dir
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         X, y, group_shapes = _data()
-        X_local, y_local, ctx = mdist.shard(X, y)
+        X_local, y_local, ctx = mdist.shard(X, y, partition=partition)
         with ctx.options(dtype=dtype, device=rank):
             t = _TrainerHandle(X_local, [], y_local, 42, _config(group_shapes, n_sweeps))
             t.init_fm(6, 0.1)
-        # 0 general level kernels, 1 field path + NCCL all-reduce, 2 field path + peer-memory exchange
-        assert t.sweep_path() == (0 if no_field else (2 if exchange == "peer" else 1)), t.sweep_path()
+        # 0 general level kernels, 1 field path + NCCL all-reduce, 2 field path + peer-memory exchange,
+        # +2 when the first field's columns are rank-exclusive (rows dealt out by column)
+        want = 0 if no_field else (2 if exchange == "peer" else 1) + (2 if partition == "column" else 0)
+        assert t.sweep_path() == want, (t.sweep_path(), want)
         states = []
         for _ in range(n_sweeps):
             t.step(1)
             states.append(_state(t))
         np.save(os.path.join(out_dir, f"states_{rank}.npy"), np.stack(states))
         np.save(os.path.join(out_dir, f"e_{rank}.npy"), t.get_e())
+        np.save(os.path.join(out_dir, f"rows_{rank}.npy"), ctx.rows)
         del t
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype,exchange,no_field", [("f64", "peer", False), ("f32", "peer", False),
-                                                    ("f64", "nccl", False), ("f64", "nccl", True)])
-def test_two_gpus_match_one(engine, dtype, exchange, no_field, tmp_path):
-    """2 row shards == 1 GPU on the whole data (f64 1e-8), replicas bit-identical, for the three
-    row-sharded schedules: field path with the statistics exchanged through peer memory, field
-    path with NCCL all-reduces, general level kernels with NCCL all-reduces."""
+@pytest.mark.parametrize("dtype,exchange,no_field,partition", [
+    ("f64", "peer", False, "column"), ("f32", "peer", False, "column"), ("f64", "nccl", False, "column"),
+    ("f64", "peer", False, "rows"), ("f32", "peer", False, "rows"), ("f64", "nccl", False, "rows"),
+    ("f64", "nccl", True, "rows"), ("f64", "nccl", True, "column")])
+def test_two_gpus_match_one(engine, dtype, exchange, no_field, partition, tmp_path):
+    """2 row shards == 1 GPU on the whole data (f64 1e-8), replicas bit-identical, for every
+    row-sharded schedule: rows dealt out by first column (the first field needs no exchange) or in
+    contiguous ranges (two passes around the exchange); statistics exchanged through peer memory
+    or NCCL all-reduces; field path or general level kernels."""
     from myfm_b200 import _lib
 
     if _lib.device_count() < 2:
@@ -87,7 +93,8 @@ def test_two_gpus_match_one(engine, dtype, exchange, no_field, tmp_path):
     from myfm_b200._myfm import _TrainerHandle
 
     n_sweeps = 4
-    mp.spawn(_worker, args=(2, _free_port(), dtype, n_sweeps, str(tmp_path), exchange, no_field), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), dtype, n_sweeps, str(tmp_path), exchange, no_field, partition), nprocs=2,
+             join=True)
     X, y, group_shapes = _data()
     with engine.engine_options(dtype=dtype):
         t = _TrainerHandle(X, [], y, 42, _config(group_shapes, n_sweeps))
@@ -100,5 +107,7 @@ def test_two_gpus_match_one(engine, dtype, exchange, no_field, tmp_path):
         want = _state(t)
         scale = np.maximum(np.abs(want), 1e-2)
         assert np.max(np.abs(got[0][it] - want) / scale) < tol, f"sweep {it}"
-    e = np.concatenate([np.load(tmp_path / f"e_{r}.npy") for r in range(2)])
+    e = np.empty(X.shape[0])
+    for r in range(2):
+        e[np.load(tmp_path / f"rows_{r}.npy")] = np.load(tmp_path / f"e_{r}.npy")
     np.testing.assert_allclose(e, t.get_e(), rtol=tol, atol=tol)
