@@ -441,7 +441,7 @@ template <typename Real> struct Trainer : TrainerBase {
   unsigned char *peer_local = nullptr;       // this rank's buffer: header, statistics buffer 0 and 1
   std::vector<unsigned char *> peer_base;    // every rank's buffer as mapped here (own: peer_local)
   size_t peer_stat_elems = 0;                // Reals per statistics buffer
-  unsigned long long peer_seq = 0;           // collectives issued so far
+
   int f_ncols0 = 0, f_ncolsL = 0;
   DevBuf<Real> f_tail_val, f_own_val, f_pend_told, f_pend_tnew, f_partial;
 
@@ -1294,7 +1294,6 @@ template <typename Real> struct Trainer : TrainerBase {
     flag.download(&ok, 1, stream);
     MYFM_CUDA(cudaStreamSynchronize(stream));
     peer_ok = ok != 0;
-    peer_seq = 0;
     peer_error.alloc(1);
     peer_error.zero(stream);
     MYFM_CUDA(cudaStreamSynchronize(stream));
@@ -1311,22 +1310,22 @@ template <typename Real> struct Trainer : TrainerBase {
     peer_local = nullptr;
     peer_ok = false;
   }
-  Real *peer_stat(int r, unsigned long long seq) const {
-    return reinterpret_cast<Real *>(peer_base[r] + PEER_HEADER_BYTES) + (seq & 1) * peer_stat_elems;
-  }
-  // Starts collective peer_seq + 1: where this rank's partial statistics go.
-  Real *peer_begin() { return peer_stat(my_rank, ++peer_seq); }
-  // Publishes them (after the producing kernel, in stream order) and describes the collective to the consumer.
-  PeerView<Real> peer_publish() {
-    k_peer_post<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long *>(peer_local), peer_seq);
-    launched();
+  Real *peer_stat(int r) const { return reinterpret_cast<Real *>(peer_base[r] + PEER_HEADER_BYTES); }
+  // header of a rank's buffer: [0] sequence number visible to the peers, [1] this rank's own counter
+  unsigned long long *peer_counter() const { return reinterpret_cast<unsigned long long *>(peer_local) + 1; }
+  PeerView<Real> peer_view() const {
     PeerView<Real> pv;
-    pv.world = world, pv.seq = peer_seq, pv.error = peer_error.p;
+    pv.world = world, pv.counter = peer_counter(), pv.elems = peer_stat_elems, pv.error = peer_error.p;
     for (int r = 0; r < world; r++) {
-      pv.stat[r] = peer_stat(r, peer_seq);
+      pv.stat[r] = peer_stat(r);
       pv.posted[r] = reinterpret_cast<const unsigned long long *>(peer_base[r]);
     }
     return pv;
+  }
+  // Publishes the statistics the preceding kernel wrote (stream order).
+  void peer_publish() {
+    k_peer_post<<<1, 1, 0, stream>>>(peer_counter(), reinterpret_cast<unsigned long long *>(peer_local));
+    launched();
   }
   DevBuf<int> peer_error;
 
@@ -1387,12 +1386,12 @@ template <typename Real> struct Trainer : TrainerBase {
       // one GPU: one fused pass.  Row shards: statistics, sum over the ranks (peer memory inside the
       // update kernel, or an NCCL all-reduce between the two), update.
       a.peer.world = 0;
+      if (peer_ok)
+        a.peer = peer_view(), a.peer_local = peer_stat(my_rank);
       const bool two_pass = world > 1 && !f_exclusive;
       for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
         const int mode = two_pass ? (pass == 0 ? FIELD_STATS : FIELD_UPDATE) : FIELD_FUSED;
         a.sched = f_sched.p + (f_launch++);
-        if (mode == FIELD_STATS && peer_ok)
-          a.colstat = peer_begin();
         if (!IS_V) {
           if (pend != PEND_NONE)
             throw std::logic_error("field path: the w sweep must not find a pending update.");
@@ -1406,7 +1405,7 @@ template <typename Real> struct Trainer : TrainerBase {
         }
         if (mode == FIELD_STATS) {
           if (peer_ok)
-            a.peer = peer_publish();
+            peer_publish();
           else
             allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncols0));
         }
@@ -1427,7 +1426,10 @@ template <typename Real> struct Trainer : TrainerBase {
       a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
       a.partial = f_partial.p, a.chunk_done = f_chunk_done.p, a.last_base = f_last_base;
       a.item_slot = f_item_slotL.p + f_levelL.s0;
-      a.colstat = world > 1 ? (peer_ok ? peer_begin() : f_colstat.p) : nullptr;
+      a.colstat = world > 1 && !peer_ok ? f_colstat.p : nullptr;
+      a.peer.world = 0, a.peer_local = nullptr;
+      if (peer_ok)
+        a.peer = peer_view(), a.peer_local = peer_stat(my_rank);
       a.pend_told = f_pend_told.p, a.pend_tnew = f_pend_tnew.p;
       const int grid = a.nS + a.nC + ceil_div(a.nW, STATS_THREADS / 32);
       if (grid) {
@@ -1438,13 +1440,11 @@ template <typename Real> struct Trainer : TrainerBase {
         launched();
       }
       if (world > 1) { // statistics of this rank's rows -> sum over the ranks -> identical draw everywhere
-        PeerView<Real> pv;
-        pv.world = 0;
         if (peer_ok)
-          pv = peer_publish();
+          peer_publish();
         else
           allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncolsL));
-        k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, pv, f_colsL.p, f_ncolsL);
+        k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, a.peer, f_colsL.p, f_ncolsL);
         launched();
       }
     }
@@ -1822,8 +1822,8 @@ template <typename Real> struct Trainer : TrainerBase {
     // Regression with the device RNG never needs the host inside a sweep: the launch sequence of a
     // slot is captured once into a CUDA graph and replayed (the very first sweep runs directly:
     // first-use allocations and function attributes are not capturable).
-    const bool graphable = device_rng && world == 1 && cfg.task_type == MYFM_TASK_REGRESSION && !timer.enabled &&
-                           use_graphs && sweep_index >= 1;
+    const bool graphable = device_rng && (world == 1 || (field_path && peer_ok)) &&
+                           cfg.task_type == MYFM_TASK_REGRESSION && !timer.enabled && use_graphs && sweep_index >= 1;
     if (graphable) {
       if (!sweep_graph[slot]) {
         const int64_t before = launches;

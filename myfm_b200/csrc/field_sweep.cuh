@@ -53,13 +53,23 @@ constexpr int PEER_MAX_RANKS = 16;
 constexpr int PEER_HEADER_BYTES = 256;
 template <typename Real> struct PeerView {
   int world = 0;                 // 0: not in use (one GPU, or NCCL all-reduce between the passes)
-  unsigned long long seq = 0;    // the collective this launch consumes
-  const Real *stat[PEER_MAX_RANKS];                 // every rank's statistics buffer of this collective
-  const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's sequence number
+  // Collectives are numbered by a counter in device memory (k_peer_post increments it), so the
+  // same launch parameters serve every sweep and the sequence can be replayed from a CUDA graph.
+  const unsigned long long *counter; // collectives published by THIS rank so far
+  size_t elems;                      // Reals per statistics buffer; collective c uses buffer c & 1
+  const Real *stat[PEER_MAX_RANKS];  // every rank's statistics buffers (buffer 0, then buffer 1)
+  const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's published sequence number
   int *error;                    // set when a peer never shows up
+  // producer: where this rank's partial statistics of the NEXT collective go
+  __device__ __forceinline__ Real *produce(Real *local_stat) const {
+    return local_stat + ((*counter + 1) & 1) * elems;
+  }
 };
 
-__global__ void k_peer_post(unsigned long long *posted, unsigned long long seq) {
+// Publishes collective *counter + 1 (runs after the producing kernel, in stream order).
+__global__ void k_peer_post(unsigned long long *counter, unsigned long long *posted) {
+  const unsigned long long seq = *counter + 1;
+  *counter = seq;
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long *>(posted) = seq;
 }
@@ -69,9 +79,10 @@ template <typename Real> __device__ __forceinline__ void peer_wait(const PeerVie
   if (pv.world == 0)
     return;
   if (threadIdx.x < pv.world) {
+    const unsigned long long seq = *pv.counter; // the collective this rank published last
     const volatile unsigned long long *flag = pv.posted[threadIdx.x];
     long long spins = 0;
-    while (*flag < pv.seq) {
+    while (*flag < seq) {
       if (++spins > (1ll << 23)) { // a few seconds of polling over NVLink
         *pv.error = 3;
         break;
@@ -84,9 +95,10 @@ template <typename Real> __device__ __forceinline__ void peer_wait(const PeerVie
 // (sq, lin) of column `slot` summed over the ranks in rank order.
 template <typename Real> __device__ __forceinline__ void peer_sum(const PeerView<Real> &pv, int slot, Real &sq, Real &lin) {
   sq = 0, lin = 0;
+  const size_t at = (*pv.counter & 1) * pv.elems + 2 * static_cast<size_t>(slot);
   for (int r = 0; r < pv.world; r++) {
-    sq += __ldcv(pv.stat[r] + 2 * slot);
-    lin += __ldcv(pv.stat[r] + 2 * slot + 1);
+    sq += __ldcv(pv.stat[r] + at);
+    lin += __ldcv(pv.stat[r] + at + 1);
   }
 }
 
@@ -114,7 +126,8 @@ template <typename Real> struct FieldStreamArgs {
   // over the ranks between the two passes
   const int *item_slot; // column slot of every item (same numbering on every rank)
   Real *colstat;        // [2 * columns of level 0]
-  PeerView<Real> peer;  // FIELD_UPDATE: where the summed statistics come from (world == 0: colstat)
+  PeerView<Real> peer;  // peer-memory exchange (world == 0: colstat holds the statistics / NCCL sums)
+  Real *peer_local;     // this rank's statistics buffers (FIELD_STATS writes the next collective's)
 };
 
 // One GPU: FIELD_FUSED (statistics, draw and update in one pass).  Row shards: the rows of a column
@@ -336,7 +349,8 @@ template <typename Real, int MODE>
 __device__ __forceinline__ void field_finish_column(const FieldStreamArgs<Real> &a, int j, int slot, Real theta_new,
                                                     Real sq, Real lin) {
   if (MODE == FIELD_STATS) {
-    a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+    Real *out = a.peer.world ? a.peer.produce(a.peer_local) : a.colstat;
+    out[2 * slot] = sq, out[2 * slot + 1] = lin;
   } else {
     a.theta[j] = theta_new;
     if (a.theta_t)
@@ -536,6 +550,8 @@ template <typename Real> struct FieldStatsArgs {
   const Real *alpha, *lambda, *mu;
   const int *item_slot; // row shards: column slot of every item; colstat [2 * columns of the level]
   Real *colstat;        // (nullptr on one GPU: the kernel draws itself)
+  PeerView<Real> peer;  // row shards with the peer-memory exchange: statistics go to peer_local
+  Real *peer_local;
   Real *partial;   // [2 nS] chunk statistics of the long columns
   int *chunk_done; // [nS] chunks finished, per long column (at its first chunk), zero between launches
   int last_base;
@@ -557,9 +573,10 @@ __device__ __forceinline__ void field_publish_draw(const FieldStatsArgs<Real> &a
 template <typename Real, bool IS_V>
 __device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int item, int j, Real sq, Real lin,
                                               Real theta_old, Real alpha) {
-  if (a.colstat) {
+  if (a.colstat || a.peer.world) {
     const int slot = a.item_slot[item];
-    a.colstat[2 * slot] = sq, a.colstat[2 * slot + 1] = lin;
+    Real *out = a.peer.world ? a.peer.produce(a.peer_local) : a.colstat;
+    out[2 * slot] = sq, out[2 * slot + 1] = lin;
   } else {
     field_publish_draw<Real, IS_V>(a, j, sq, lin, theta_old, alpha);
   }
