@@ -92,14 +92,20 @@ template <typename Real> __device__ __forceinline__ void peer_wait(const PeerVie
   }
   __syncthreads();
 }
-// (sq, lin) of column `slot` summed over the ranks in rank order.
+// (sq, lin) of column `slot` summed over the ranks in rank order.  All remote loads are issued
+// before the first add: a load-add-load-add loop would pay the NVLink latency once per rank.
 template <typename Real> __device__ __forceinline__ void peer_sum(const PeerView<Real> &pv, int slot, Real &sq, Real &lin) {
-  sq = 0, lin = 0;
   const size_t at = (*pv.counter & 1) * pv.elems + 2 * static_cast<size_t>(slot);
-  for (int r = 0; r < pv.world; r++) {
-    sq += __ldcv(pv.stat[r] + at);
-    lin += __ldcv(pv.stat[r] + at + 1);
-  }
+  Pair<Real> v[PEER_MAX_RANKS];
+#pragma unroll
+  for (int r = 0; r < PEER_MAX_RANKS; r++)
+    if (r < pv.world)
+      v[r] = __ldcv(reinterpret_cast<const Pair<Real> *>(pv.stat[r] + at));
+  sq = 0, lin = 0;
+#pragma unroll
+  for (int r = 0; r < PEER_MAX_RANKS; r++)
+    if (r < pv.world)
+      sq += v[r].x, lin += v[r].y;
 }
 
 template <typename Real> struct FieldStreamArgs {
