@@ -118,6 +118,34 @@ def cpu_baseline(X, y, group_shapes, rank, budget_s: float = 20.0):
                       f"{os.cpu_count()} cores)"}
 
 
+def ncu_traffic(rank: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two column-sweep kernels from the newest
+    committed `ncu --set full` capture (profiles/*_full_raw.csv), per sweep: (rank + 1) launches each."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_full_raw.csv")))
+    if not files:
+        return None, None
+    rows = list(csv.reader(open(files[-1])))
+    hdr, units = rows[0], rows[1]
+    try:
+        i_name, i_rd, i_wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_kernel = {}
+    for r in rows[2:]:
+        for key in ("k_field_stream", "k_field_stats"):
+            if key in r[i_name]:
+                b = float(r[i_rd]) * scale.get(units[i_rd], 1.0) + float(r[i_wr]) * scale.get(units[i_wr], 1.0)
+                per_kernel.setdefault(key, []).append(b)
+    if len(per_kernel) < 2:
+        return None, None
+    per_vector = sum(sum(v) / len(v) for v in per_kernel.values())
+    return per_vector * (rank + 1), os.path.relpath(files[-1], ROOT)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation (oracle port; the reference cannot be
     built without Eigen) on the host cores it can use (one: the sampler is single-threaded)."""
@@ -273,6 +301,8 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = bytes_["sweeps"] * args.steps / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else None
+    traffic, traffic_src = ncu_traffic(rank) if (sweep_path >= 1 and args.gpus == 1 and args.workload == "ml10m"
+                                                 and dtype == "f32") else (None, None)
     line = {
         "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -288,7 +318,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "traffic_source": (f"{traffic_src}: dram read+write of k_field_stream + k_field_stats per launch x "
+                                        f"{rank + 1} vectors per sweep (bytes per step, like algorithmic_bytes_per_step)")
+                     if traffic else None, "peak_source": peak_src,
                      "kernel": ("k_field_stream + k_field_stats (column sweeps of w and of the K factor columns: "
                                 "streaming level with fused q_init, gather-only last level)" if sweep_path == 1 else
                                 "k_level_sweep + k_level_seg_update (column sweeps of w and of the K factor columns"

@@ -1369,6 +1369,12 @@ template <typename Real> struct Trainer : TrainerBase {
       FieldStreamArgs<Real> a;
       a.item = reinterpret_cast<const int4 *>(f_items0.p + f_level0.s0);
       a.nCC = f_nCC, a.nCR = f_nCR, a.nG = f_nG, a.nW = f_nW;
+      { // about four scheduling steps per warp: large batches amortise the counter, small ones the tail
+        const char *env = std::getenv("MYFM_FIELD_BATCH");
+        const int warps = f_sm_count * FIELD_WARPS;
+        int b = env ? std::atoi(env) : ceil_div(f_nW, 4 * static_cast<int64_t>(warps));
+        a.batch = std::max(1, std::min(b, FIELD_BATCH_MAX));
+      }
       a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
       a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;
       a.tail_last = f_tail_idx.p + static_cast<int64_t>(f_tail - 1) * N;

@@ -28,7 +28,7 @@ namespace myfm {
 
 constexpr int FIELD_THREADS = 1024; // streaming pass: one persistent CTA per SM
 // rows per lane kept in registers between the reduction and the update: 8 (f32), 4 (f64)
-constexpr int FIELD_BATCH = 8;       // level-0 columns a warp takes per scheduling step (at most 32)
+constexpr int FIELD_BATCH_MAX = 8;   // level-0 columns a warp takes per scheduling step (a.batch, at most 32)
 constexpr int FIELD_CTA_MAX = 32768;  // longest level-0 column (one CTA); longer: general path
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_WARP_MAX = 2048;  // last level: warp per column up to here (no barrier on the path),
@@ -111,6 +111,7 @@ template <typename Real> __device__ __forceinline__ void peer_sum(const PeerView
 template <typename Real> struct FieldStreamArgs {
   const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
   int nCC, nCR, nG, nW;
+  int batch;        // warp columns taken per scheduling step: 1 .. FIELD_BATCH_MAX (few columns: small batches)
   int *sched;       // work counter of the warp items (zero at launch)
   Pair<Real> *eq;
   int64_t n_rows;
@@ -490,6 +491,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   const int total_warps = gridDim.x * FIELD_WARPS;
   const int first_w = a.nCC + a.nCR + a.nG;
   const int4 *items_w = a.item + first_w;
+  const int FIELD_BATCH = a.batch;
   int kb = (blockIdx.x + gridDim.x * warp) * FIELD_BATCH; // longest columns spread over the SMs
   while (kb < a.nW) {
     int kb_next = 0;

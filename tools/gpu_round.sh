@@ -14,7 +14,9 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2
 cat gpurun_out/bench_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py --sweeps 2 > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_field_stream|k_field_stats|k_predict_tile|k_mt_generate" -s 60 -c 8 \
-    -o gpurun_out/full_$TAG -f python tools/profile_step.py --sweeps 3 > gpurun_out/ncu_full.log 2>&1
+# full-set capture of the hot kernels; the report stays on the box, its raw page comes back as CSV
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_field_stream|k_field_stats|k_predict_tile" -s 40 -c 5 \
+    -o /tmp/full_$TAG -f python tools/profile_step.py --sweeps 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
-ls -la gpurun_out/
+ncu -i /tmp/full_$TAG.ncu-rep --page raw --csv > gpurun_out/full_${TAG}_raw.csv 2>/dev/null
+ls -la gpurun_out/ /tmp/full_$TAG.ncu-rep

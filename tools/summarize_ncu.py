@@ -51,7 +51,10 @@ FULL = [
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # already the raw page
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print("| kernel | " + " | ".join(n for _, n in FULL) + " |\n|---|" + "---|" * len(FULL))
