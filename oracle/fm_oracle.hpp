@@ -16,8 +16,9 @@
 // The reference ships no golden vectors and cannot itself be run here (it needs Eigen 3.4.0,
 // fetched from the network by setup.py:21-50; Eigen is not installed, there is no network), so
 // nothing tighter exists to pin against: what those tests do not constrain — the order of Eigen's
-// vectorised dense reductions (O(eps)) and the column-major fill order of FM.hpp:34-45 — is an
-// assumption of the restatement, stated in every parity report.
+// vectorised dense reductions (restated from Eigen 3.4.0's Redux.h for an SSE2 build, see
+// eigen_dense_sum) and the column-major fill order of FM.hpp:34-45 — is an assumption of the
+// restatement, stated in every parity report.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // RNG: std::mt19937 + libstdc++ distributions constructed exactly where the reference constructs
@@ -47,6 +48,52 @@ extern double erf(double x);
 namespace oracle {
 
 enum class Task : int { REGRESSION = 0, CLASSIFICATION = 1, ORDERED = 2 };
+
+// Sum of f(0) .. f(n-1) in the order of Eigen's dense vectorised reduction, which is what the
+// reference's two dense `.sum()` calls run (FMTrainer.hpp:138, :223).  Eigen 3.4.0 (the version
+// setup.py:21-23 pins; not available here) implements it in Eigen/src/Core/Redux.h as
+// redux_impl<Func, Evaluator, LinearVectorizedTraversal, NoUnrolling>, restated from the published
+// source: two packet accumulators walk the vector in strides of two packets, are added, a last
+// odd packet is added, the packet is reduced horizontally, and the scalar tail follows.  A default
+// `pip install` of the reference compiles without -march, i.e. SSE2: 16-byte packets (4 floats,
+// 2 doubles), predux = (a0 + a2) + (a1 + a3) for floats and a0 + a1 for doubles
+// (Eigen/src/Core/arch/SSE/PacketMath.h).  Both expressions are coefficient-wise ops without
+// direct access, so the aligned start is 0.  For double this differs from a serial loop at the
+// 1e-16 level; for float over 10^7 rows a serial accumulator is off by 1e-3, so the order matters.
+template <typename Real, typename F> Real eigen_dense_sum(size_t n, F f) {
+  constexpr size_t P = 16 / sizeof(Real);
+  if (n == 0)
+    return Real(0); // Eigen returns Scalar(0) for an empty sum (DenseBase::sum)
+  const size_t aligned2 = (n / (2 * P)) * (2 * P), aligned = (n / P) * P;
+  Real res;
+  if (aligned) {
+    Real p0[P], p1[P];
+    for (size_t k = 0; k < P; k++)
+      p0[k] = f(k);
+    if (aligned > P) {
+      for (size_t k = 0; k < P; k++)
+        p1[k] = f(P + k);
+      for (size_t i = 2 * P; i < aligned2; i += 2 * P)
+        for (size_t k = 0; k < P; k++) {
+          p0[k] += f(i + k);
+          p1[k] += f(i + P + k);
+        }
+      for (size_t k = 0; k < P; k++)
+        p0[k] += p1[k];
+      if (aligned > aligned2)
+        for (size_t k = 0; k < P; k++)
+          p0[k] += f(aligned2 + k);
+    }
+    res = P == 4 ? (p0[0] + p0[2 % P]) + (p0[1] + p0[3 % P]) : p0[0] + p0[1];
+    for (size_t i = aligned; i < n; i++)
+      res += f(i);
+  } else {
+    res = f(0);
+    for (size_t i = 1; i < n; i++)
+      res += f(i);
+  }
+  return res;
+}
 
 // Row-compressed sparse matrix; stands in for Eigen::SparseMatrix<Real, RowMajor>
 // (include/myfm/definitions.hpp:22-23).  Indices are taken as given: not sorted, duplicates kept.
@@ -921,9 +968,7 @@ template <typename Real> struct Trainer {
       hyper.alpha = static_cast<Real>(1);
       return;
     }
-    Real e_all = 0;
-    for (Real v : e_train)
-      e_all += v * v;
+    Real e_all = eigen_dense_sum<Real>(e_train.size(), [&](size_t i) { return e_train[i] * e_train[i]; }); // :138
     Real exponent = (static_cast<Real>(cfg.alpha_0) + X.rows) / 2;
     Real variance = (static_cast<Real>(cfg.beta_0) + e_all) / 2;
     hyper.alpha = std::gamma_distribution<Real>(exponent, 1 / variance)(gen_);
@@ -966,9 +1011,7 @@ template <typename Real> struct Trainer {
       fm.w0 = 0; // NB: e_train keeps the stale contribution until update_e
       return;
     }
-    Real s = 0;
-    for (Real v : e_train)
-      s += (fm.w0 - v);
+    Real s = eigen_dense_sum<Real>(e_train.size(), [&](size_t i) { return fm.w0 - e_train[i]; }); // :223
     Real lin = hyper.alpha * s;
     Real quad = hyper.alpha * n_train + static_cast<Real>(cfg.reg_0);
     Real w0_new = sample_normal(quad, lin);
