@@ -7,6 +7,7 @@
 #include "host_data.hpp"
 #include "kernels.cuh"
 #include "field_sweep.cuh"
+#include "latent_device.cuh"
 #include "mt_device.cuh"
 #include "oprobit.cuh"
 #include "rng.hpp"
@@ -463,6 +464,11 @@ template <typename Real> struct Trainer : TrainerBase {
   DevBuf<int> group, feat_ptr, feat_idx;
 
   MtStream<Real> rng;
+  // MYFM_RNG_PHILOX: the per-row latent draws of classification / ordered probit run on the device
+  // from counter-based streams (latent_device.cuh); the sweep's Gaussian / Gamma variates still come
+  // from the (device-side) mt19937 stream, which the latent draws then no longer touch.
+  bool philox_latents = false;
+  uint64_t latent_seed = 0;
   SweepLayout layout;
   DevBuf<Real> z_dev;
   PinnedBuf<Real> z_pinned[2];
@@ -500,8 +506,10 @@ template <typename Real> struct Trainer : TrainerBase {
           int64_t n_y, int seed, const myfm_config_t &cfg_api, const myfm_engine_options_t &o)
       : cfg(cfg_api), opt(o), device(o.device), rng(seed) {
     dtype = o.dtype;
-    if (o.rng != MYFM_RNG_MT19937)
-      throw std::runtime_error("rng=philox is not available in this build; use rng=mt19937.");
+    if (o.rng != MYFM_RNG_MT19937 && o.rng != MYFM_RNG_PHILOX)
+      throw std::invalid_argument("unknown rng.");
+    philox_latents = o.rng == MYFM_RNG_PHILOX;
+    latent_seed = (static_cast<uint64_t>(static_cast<uint32_t>(seed)) << 32) ^ 0x9E3779B97F4A7C15ull;
     world = o.world_size > 1 ? o.world_size : 1;
     if (world > 1) {
       if (!o.nccl_unique_id)
@@ -808,7 +816,7 @@ template <typename Real> struct Trainer : TrainerBase {
   void setup_rng() {
     MYFM_CUDA(cudaStreamSynchronize(rng_stream));
     const char *force_host = std::getenv("MYFM_HOST_RNG");
-    device_rng = cfg.task_type == MYFM_TASK_REGRESSION && shape_alpha >= 1 &&
+    device_rng = (cfg.task_type == MYFM_TASK_REGRESSION || philox_latents) && shape_alpha >= 1 &&
                  !(force_host && force_host[0] == '1');
     for (Real sh : shapes_lw)
       device_rng = device_rng && sh >= 1;
@@ -1604,6 +1612,14 @@ template <typename Real> struct Trainer : TrainerBase {
   // update_e for classification (FMTrainer.hpp:498-512): the truncated-normal draws consume the
   // mt19937 stream row by row, data dependently, so in MT19937 mode they run on the host.
   void classification_latent() {
+    if (philox_latents) {
+      if (N) {
+        k_latent_classification<Real><<<ceil_div(N, 256), 256, 0, stream>>>(
+            N, eq(), y.p, perm_dev.p, latent_seed, static_cast<uint32_t>(sweep_index + 1));
+        launched();
+      }
+      return;
+    }
     e_host.resize(N);
     export_component(0, e_host.data()); // caller's row order: the stream is consumed row by row
     const Real zero = 0, sd = 1;
@@ -1689,6 +1705,26 @@ template <typename Real> struct Trainer : TrainerBase {
   void ordered_update(bool start) {
     if (start)
       build_cut_groups();
+    if (philox_latents) { // cut-point move on the host (device row sums), latent z on the device
+      for (CutGroup &cg : cut_groups) {
+        if (start)
+          cg.sampler->start();
+        else
+          cg.sampler->step(rng.gen);
+        cg.cutpoints = cg.sampler->gamma_now;
+        const int n_group = static_cast<int>(cg.rows.size());
+        if (!n_group)
+          continue;
+        MYFM_CUDA(cudaStreamSynchronize(stream)); // lat_gamma may still be read by the previous group's kernel
+        lat_gamma.upload(cg.cutpoints, stream);
+        k_latent_ordered<Real><<<ceil_div(n_group, 256), 256, 0, stream>>>(
+            cg.n_class, cg.class_ptr.p, cg.class_rows.p, lat_gamma.p, eq(), perm_dev.p, latent_seed,
+            start ? 0u : static_cast<uint32_t>(sweep_index + 1));
+        launched();
+      }
+      MYFM_CUDA(cudaStreamSynchronize(stream)); // host staging of the cut-points dies with this call
+      return;
+    }
     e_host.resize(N);
     export_component(0, e_host.data());
     for (CutGroup &cg : cut_groups) {
@@ -1716,6 +1752,7 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     import_component(0, e_host.data());
   }
+  DevBuf<Real> lat_gamma;
 
   // eq component (0 = e, 1 = q) <-> a dense host vector in the caller's row order
   void export_component(int comp, Real *host) {
