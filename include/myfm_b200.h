@@ -50,8 +50,11 @@ extern "C" {
  * MT19937: the engine consumes the libstdc++ std::mt19937(seed) stream draw for draw in the
  *          reference's order, so chains are comparable with the reference on
  *          the same seed.
- * PHILOX : counter-based device RNG keyed by (seed, iteration, step, index); statistically
- *          equivalent chain, no host involvement. */
+ * PHILOX : the per-row latent draws of classification / ordered probit (FMTrainer.hpp:498-521,
+ *          util.hpp:15-78) come from counter-based Philox4x32-10 streams on the device, keyed by
+ *          (seed; row, sweep, attempt); the sweep's Gaussian / Gamma variates still follow the
+ *          mt19937 stream.  Statistically equivalent chain, no host involvement inside a sweep;
+ *          regression chains are identical in both modes. */
 #define MYFM_RNG_MT19937 0
 #define MYFM_RNG_PHILOX 1
 
