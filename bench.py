@@ -167,7 +167,7 @@ def run_reference(args):
         "impl": "reference", "metric": "gibbs_iterations_per_sec", "value": value, "unit": "it/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
         "steps_run": steps, "warmup_run": 1 + warm,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, X.shape[0], X.nnz, rank, args.gpus),
         "nnz_rank_per_sec": value * X.nnz * rank,
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": 1, "kind": "port",

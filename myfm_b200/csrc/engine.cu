@@ -1104,7 +1104,7 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     MYFM_CUDA(cudaDeviceGetAttribute(&f_sm_count, cudaDevAttrMultiProcessorCount, device));
     const int64_t tab = static_cast<int64_t>(hi) - lo + 1;
-    if (tab * 3 * static_cast<int64_t>(sizeof(Real)) > dev_smem - 2048)
+    if (tab * FieldTab<Real>::BYTES_PER_COLUMN > dev_smem - 4096)
       return;
     f_last_base = lo, f_tab = static_cast<int>(tab), f_tail = L - 1;
 
@@ -1355,7 +1355,7 @@ template <typename Real> struct Trainer : TrainerBase {
   template <bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE>
   void launch_field_stream_as(const FieldStreamArgs<Real> &a) {
     auto kernel = k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND, MODE>;
-    const size_t smem = 3 * static_cast<size_t>(f_tab) * sizeof(Real);
+    const size_t smem = static_cast<size_t>(f_tab) * FieldTab<Real>::BYTES_PER_COLUMN;
     static size_t configured = 0; // per instantiation
     if (smem > configured) {
       MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1382,6 +1382,8 @@ template <typename Real> struct Trainer : TrainerBase {
         const int warps = f_sm_count * FIELD_WARPS;
         int b = env ? std::atoi(env) : ceil_div(f_nW, 4 * static_cast<int64_t>(warps));
         a.batch = std::max(1, std::min(b, FIELD_BATCH_MAX));
+        const char *pf = std::getenv("MYFM_FIELD_PREFETCH");
+        a.prefetch = pf ? std::atoi(pf) : 0; // measured: no gain on B200 (the pass is issue-bound, not latency-bound)
       }
       a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
       a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;

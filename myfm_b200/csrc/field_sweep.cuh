@@ -112,6 +112,7 @@ template <typename Real> struct FieldStreamArgs {
   const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
   int nCC, nCR, nG, nW;
   int batch;        // warp columns taken per scheduling step: 1 .. FIELD_BATCH_MAX (few columns: small batches)
+  int prefetch;     // pull the rows of a batch into L2 before its first column starts
   int *sched;       // work counter of the warp items (zero at launch)
   Pair<Real> *eq;
   int64_t n_rows;
@@ -143,6 +144,31 @@ template <typename Real> struct FieldStreamArgs {
 // (identically on every rank) and writes e, q.
 enum { FIELD_FUSED = 0, FIELD_STATS = 1, FIELD_UPDATE = 2 };
 
+// Shared-memory table of the last level's columns: {theta_old, theta_new} of the update left
+// pending and theta of the vector being swept.  f32: one 16-byte record per column (one LDS.128 per
+// row instead of three scattered LDS.32); f64: three arrays.
+template <typename Real> struct FieldTab;
+template <> struct FieldTab<float> {
+  static constexpr int BYTES_PER_COLUMN = 16;
+  static __device__ __forceinline__ void get(const float *base, int, int j, float &told, float &tnew, float &tnext) {
+    const float4 r = reinterpret_cast<const float4 *>(base)[j];
+    told = r.x, tnew = r.y, tnext = r.z;
+  }
+  static __device__ __forceinline__ void put(float *base, int, int j, float told, float tnew, float tnext) {
+    reinterpret_cast<float4 *>(base)[j] = make_float4(told, tnew, tnext, 0.f);
+  }
+};
+template <> struct FieldTab<double> {
+  static constexpr int BYTES_PER_COLUMN = 24;
+  static __device__ __forceinline__ void get(const double *base, int n, int j, double &told, double &tnew,
+                                             double &tnext) {
+    told = base[j], tnew = base[n + j], tnext = base[2 * n + j];
+  }
+  static __device__ __forceinline__ void put(double *base, int n, int j, double told, double tnew, double tnext) {
+    base[j] = told, base[n + j] = tnew, base[2 * n + j] = tnext;
+  }
+};
+
 // U rows of the streaming pass in flight per thread: all global loads are issued first (load),
 // the shared-memory lookups and the arithmetic follow (finish) — a row's table index comes out of
 // its own load, so interleaving the two would serialise the rows on the memory latency.
@@ -166,17 +192,17 @@ template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U> st
 
   // Row i as the level-0 column sees it: e with the pending update applied, q = x_i . V[:, r]
   // (IS_V; the stored q otherwise) and the row's level-0 value x0.
-  __device__ __forceinline__ void finish(const FieldStreamArgs<Real> &a, const Real *s_told, const Real *s_tnew,
-                                         const Real *s_tnext, int u, int i, Real theta_old, Real &e, Real &q,
+  __device__ __forceinline__ void finish(const FieldStreamArgs<Real> &a, const Real *s_tab, int u, int i, Real theta_old, Real &e, Real &q,
                                          Real &x0_out) const {
     e = v[u].x, q = v[u].y, x0_out = x0[u];
     const Real xlu = xl[u];
+    Real told = 0, tnew = 0, tnext = 0;
+    if (NEED_LAST)
+      FieldTab<Real>::get(s_tab, a.n_tab, jl[u], told, tnew, tnext);
     if (PEND == PEND_V) { // FMTrainer.hpp:366-374 of the previous factor's last-level column
-      const Real told = s_told[jl[u]], tnew = s_tnew[jl[u]];
       const Real h = xlu * (q - xlu * told);
       e = e + h * (tnew - told);
     } else if (PEND == PEND_W) { // FMTrainer.hpp:240,251
-      const Real told = s_told[jl[u]], tnew = s_tnew[jl[u]];
       e = (e - xlu * told) + xlu * tnew;
     }
     if (IS_V) { // q_init in CSR order (FMTrainer.hpp:320)
@@ -189,7 +215,7 @@ template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U> st
           acc += x * a.theta[__ldcs(a.tail_idx + off)];
         }
       }
-      acc += xlu * s_tnext[jl[u]];
+      acc += xlu * tnext;
       q = acc;
     }
   }
@@ -227,8 +253,7 @@ __device__ __forceinline__ Pair<Real> field_update(Real e, Real q, Real x0, Real
 // One pass of NT cooperating threads (t = 0 .. NT-1) over the rows [lo, hi) of a column, U rows
 // per thread in flight.  UPDATE = false: accumulates the statistics; true: writes e and q back.
 template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int NT, bool UPDATE>
-__device__ __forceinline__ void field_pass(const FieldStreamArgs<Real> &a, const Real *s_told,
-                                           const Real *s_tnew, const Real *s_tnext, int lo, int hi, int t,
+__device__ __forceinline__ void field_pass(const FieldStreamArgs<Real> &a, const Real *s_tab, int lo, int hi, int t,
                                            Real theta_old, Real theta_new, Real alpha, Real &sq, Real &lin) {
   constexpr int U = 4;
   for (int base = lo + t; base < hi; base += U * NT) {
@@ -241,7 +266,7 @@ __device__ __forceinline__ void field_pass(const FieldStreamArgs<Real> &a, const
       const int i = base + u * NT;
       if (i < hi) {
         Real e, q, x0;
-        b.finish(a, s_told, s_tnew, s_tnext, u, i, theta_old, e, q, x0);
+        b.finish(a, s_tab, u, i, theta_old, e, q, x0);
         if (UPDATE)
           __stcg(a.eq + i, field_update<Real, IS_V>(e, q, x0, theta_old, theta_new));
         else
@@ -284,8 +309,7 @@ __device__ __forceinline__ void field_group_sum(Real &sq, Real &lin, Real *s_par
 // FULL: slots 0 .. NS-2 hold a row in every thread (the caller picked NS = ceil(rows / threads)),
 // only the last slot is ragged; otherwise every slot is checked.
 template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW, int NS, bool FULL>
-__device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a, const Real *s_told,
-                                                  const Real *s_tnew, const Real *s_tnext, int4 it, int t,
+__device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a, const Real *s_tab, int4 it, int t,
                                                   Real theta_old, Real alpha, Real lam, Real mu, Real z,
                                                   Real *s_part, int parity, int grp, int wig, int lane,
                                                   Real theta_given, Real &sq, Real &lin) {
@@ -302,7 +326,7 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
   sq = 0, lin = 0;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
-    b.finish(a, s_told, s_tnew, s_tnext, s, ok[s] ? i0 + NT * s : it.z - 1, theta_old, e[s], q[s], x0[s]);
+    b.finish(a, s_tab, s, ok[s] ? i0 + NT * s : it.z - 1, theta_old, e[s], q[s], x0[s]);
     if (MODE != FIELD_UPDATE && ok[s])
       field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
   }
@@ -321,8 +345,7 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
 
 // Picks the instantiation for the column's slot count (warp-uniform switch).
 template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW>
-__device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real> &a, const Real *s_told,
-                                                      const Real *s_tnew, const Real *s_tnext, int4 it, int t,
+__device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real> &a, const Real *s_tab, int4 it, int t,
                                                       Real theta_old, Real alpha, Real lam, Real mu, Real z,
                                                       Real *s_part, int parity, int grp, int wig, int lane,
                                                       Real theta_given, Real &sq, Real &lin) {
@@ -331,7 +354,7 @@ __device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real
 #define MYFM_SLOTS(NS)                                                                             \
   case NS:                                                                                         \
     return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, GW, (NS <= R ? NS : R), true>(                 \
-        a, s_told, s_tnew, s_tnext, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane,           \
+        a, s_tab, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane,           \
         theta_given, sq, lin);
   switch (n_slots) {
     MYFM_SLOTS(1)
@@ -375,13 +398,10 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ Real scratch[32];
   __shared__ Real s_part_cta[2 * FIELD_WARPS * 2], s_part_grp[2 * FIELD_WARPS * 2];
-  Real *s_told = reinterpret_cast<Real *>(s_raw), *s_tnew = s_told + a.n_tab, *s_tnext = s_tnew + a.n_tab;
-  for (int t = threadIdx.x; t < a.n_tab; t += FIELD_THREADS) {
-    if (PEND != PEND_NONE)
-      s_told[t] = a.pend_told[t], s_tnew[t] = a.pend_tnew[t];
-    if (IS_V)
-      s_tnext[t] = a.theta[a.last_base + t];
-  }
+  Real *s_tab = reinterpret_cast<Real *>(s_raw);
+  for (int t = threadIdx.x; t < a.n_tab; t += FIELD_THREADS)
+    FieldTab<Real>::put(s_tab, a.n_tab, t, PEND != PEND_NONE ? a.pend_told[t] : Real(0),
+                        PEND != PEND_NONE ? a.pend_tnew[t] : Real(0), IS_V ? a.theta[a.last_base + t] : Real(0));
   __syncthreads();
   const Real alpha = *a.alpha;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -405,7 +425,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
     Real sq = 0, lin = 0, theta_new = theta_old;
     if (MODE != FIELD_UPDATE) {
-      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_tab, it.y, it.z,
                                                                         threadIdx.x, theta_old, theta_old, alpha, sq,
                                                                         lin);
       sq = block_sum(sq, scratch);
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       } else {
         theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
       }
-      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_told, s_tnew, s_tnext, it.y, it.z,
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_tab, it.y, it.z,
                                                                        threadIdx.x, theta_old, theta_new, alpha, sq,
                                                                        lin);
     }
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
         given = __shfl_sync(FULL_MASK, given, 0);
       }
       const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_WARPS, R, false>(
-          a, s_told, s_tnew, s_tnext, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane,
+          a, s_tab, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane,
           given, sq, lin);
       if (MODE == FIELD_UPDATE)
         __syncthreads(); // every thread has read theta[j] (the other modes synchronise in the reduction)
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
         given = __shfl_sync(FULL_MASK, given, 0);
       }
       const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_GROUP_WARPS>(
-          a, s_told, s_tnew, s_tnext, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
+          a, s_tab, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
           lane, given, sq, lin);
       if (MODE == FIELD_UPDATE) // every warp of the group has read theta[j] before it changes
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(FIELD_GROUP_WARPS * 32) : "memory");
@@ -512,7 +532,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       if (MODE == FIELD_UPDATE)
         my_given = draw_given(my_slot, my_theta, my_lam, my_mu, my_z);
     }
-    for (int bi = 0; bi < n_batch; bi++) {
+    for (int bi = 0; bi < (a.prefetch ? n_batch : 0); bi++) {
       const int lo = __shfl_sync(FULL_MASK, my_it.y, bi), n = __shfl_sync(FULL_MASK, my_it.z, bi) - lo;
       const char *p_eq = reinterpret_cast<const char *>(a.eq + lo);
       for (int off = lane * 128; off < n * static_cast<int>(sizeof(Pair<Real>)); off += 32 * 128)
@@ -533,7 +553,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       const int slot = MODE == FIELD_FUSED ? 0 : __shfl_sync(FULL_MASK, my_slot, bi);
       Real sq, lin;
       const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, 1>(
-          a, s_told, s_tnew, s_tnext, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin);
+          a, s_tab, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin);
       if (lane == 0)
         field_finish_column<Real, MODE>(a, it.x, slot, theta_new, sq, lin);
     }
