@@ -1324,16 +1324,13 @@ template <typename Real> struct Trainer : TrainerBase {
   PeerView<Real> peer_view() const {
     PeerView<Real> pv;
     pv.world = world, pv.counter = peer_counter(), pv.elems = peer_stat_elems, pv.error = peer_error.p;
+    pv.my_posted = reinterpret_cast<unsigned long long *>(peer_local);
+    pv.done = reinterpret_cast<unsigned int *>(peer_local + 16);
     for (int r = 0; r < world; r++) {
       pv.stat[r] = peer_stat(r);
       pv.posted[r] = reinterpret_cast<const unsigned long long *>(peer_base[r]);
     }
     return pv;
-  }
-  // Publishes the statistics the preceding kernel wrote (stream order).
-  void peer_publish() {
-    k_peer_post<<<1, 1, 0, stream>>>(peer_counter(), reinterpret_cast<unsigned long long *>(peer_local));
-    launched();
   }
   DevBuf<int> peer_error;
 
@@ -1420,9 +1417,7 @@ template <typename Real> struct Trainer : TrainerBase {
           MYFM_FS(true, PEND_V)
         }
         if (mode == FIELD_STATS) {
-          if (peer_ok)
-            peer_publish();
-          else
+          if (!peer_ok) // with the peer exchange the producing kernel's last CTA has published already
             allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncols0));
         }
       }
@@ -1456,9 +1451,7 @@ template <typename Real> struct Trainer : TrainerBase {
         launched();
       }
       if (world > 1) { // statistics of this rank's rows -> sum over the ranks -> identical draw everywhere
-        if (peer_ok)
-          peer_publish();
-        else
+        if (!peer_ok)
           allreduce_sum(f_colstat.p, 2 * static_cast<size_t>(f_ncolsL));
         k_field_draw_last<Real, IS_V><<<ceil_div(f_ncolsL, 256), 256, 0, stream>>>(a, a.peer, f_colsL.p, f_ncolsL);
         launched();

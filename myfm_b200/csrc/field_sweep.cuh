@@ -43,7 +43,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // the kernels through peer memory instead of being a collective of its own.  Every rank owns a
 // buffer that all peers map (cudaIpc): a header with the sequence number of the last collective
 // whose local statistics are complete, then two statistics buffers used alternately.  The
-// producing kernel writes this rank's partial sums into its own buffer, k_peer_post publishes the
+// producing kernel writes this rank's partial sums into its own buffer and its last CTA publishes the
 // sequence number, and the consuming kernel — after seeing the sequence number on every peer —
 // reads the partial sums of ALL ranks straight over NVLink and adds them in rank order, so every
 // rank forms bit-identical sums.  A rank cannot run two collectives ahead of a peer (it needs the
@@ -53,9 +53,11 @@ constexpr int PEER_MAX_RANKS = 16;
 constexpr int PEER_HEADER_BYTES = 256;
 template <typename Real> struct PeerView {
   int world = 0;                 // 0: not in use (one GPU, or NCCL all-reduce between the passes)
-  // Collectives are numbered by a counter in device memory (k_peer_post increments it), so the
+  // Collectives are numbered by a counter in device memory (peer_post_when_last increments it), so the
   // same launch parameters serve every sweep and the sequence can be replayed from a CUDA graph.
-  const unsigned long long *counter; // collectives published by THIS rank so far
+  unsigned long long *counter;       // collectives published by THIS rank so far
+  unsigned long long *my_posted;     // where this rank publishes that number for the peers
+  unsigned int *done;                // CTAs of the producing kernel that have finished (zero between launches)
   size_t elems;                      // Reals per statistics buffer; collective c uses buffer c & 1
   const Real *stat[PEER_MAX_RANKS];  // every rank's statistics buffers (buffer 0, then buffer 1)
   const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's published sequence number
@@ -66,12 +68,22 @@ template <typename Real> struct PeerView {
   }
 };
 
-// Publishes collective *counter + 1 (runs after the producing kernel, in stream order).
-__global__ void k_peer_post(unsigned long long *counter, unsigned long long *posted) {
-  const unsigned long long seq = *counter + 1;
-  *counter = seq;
-  __threadfence_system();
-  *reinterpret_cast<volatile unsigned long long *>(posted) = seq;
+// End of a producing kernel: the CTA that finishes last publishes collective *counter + 1 (no
+// separate launch).  Called by every thread of every CTA after its last statistics store.
+template <typename Real> __device__ __forceinline__ void peer_post_when_last(const PeerView<Real> &pv) {
+  if (pv.world == 0)
+    return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence(); // this CTA's statistics before the count
+    if (atomicAdd(pv.done, 1u) == gridDim.x - 1) {
+      *pv.done = 0;
+      const unsigned long long seq = *pv.counter + 1;
+      *pv.counter = seq;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long *>(pv.my_posted) = seq;
+    }
+  }
 }
 
 // Block-wide: returns once every rank has published `seq` (bounded: a dead peer raises the error flag).
@@ -559,6 +571,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     }
     kb = __shfl_sync(FULL_MASK, kb_next, 0);
   }
+  if (MODE == FIELD_STATS)
+    peer_post_when_last(a.peer);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,12 +649,11 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
   const bool cta_item = b < a.nS + a.nC;
   const int lane = threadIdx.x & 31;
   const int w = (b - a.nS - a.nC) * (STATS_THREADS / 32) + (threadIdx.x >> 5);
-  if (!cta_item && w >= a.nW)
-    return;
-  const int4 it = __ldg(a.item + (cta_item ? b : a.nS + a.nC + w));
+  const bool idle = !cta_item && w >= a.nW; // a warp beyond the last column (stays for the final barrier)
+  const int4 it = idle ? make_int4(0, 0, 0, 0) : __ldg(a.item + (cta_item ? b : a.nS + a.nC + w));
   const int j = it.x;
   const Real alpha = *a.alpha;
-  const Real theta_old = a.theta[j];
+  const Real theta_old = idle ? Real(0) : a.theta[j];
   const int t = cta_item ? threadIdx.x : lane, nt = cta_item ? STATS_THREADS : 32;
   Real sq = 0, lin = 0;
   constexpr int U = 8; // gathers in flight per thread
@@ -685,12 +698,13 @@ __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Re
         field_publish<Real, IS_V>(a, b, j, sq, lin, theta_old, alpha);
       }
     }
-  } else {
+  } else if (!idle) {
     sq = warp_sum(sq);
     lin = warp_sum(lin);
     if (lane == 0)
       field_publish<Real, IS_V>(a, a.nS + a.nC + w, j, sq, lin, theta_old, alpha);
   }
+  peer_post_when_last(a.peer);
 }
 
 } // namespace myfm
