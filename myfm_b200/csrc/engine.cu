@@ -1127,6 +1127,27 @@ template <typename Real> struct Trainer : TrainerBase {
       else
         f_nW++;
     }
+    // Inside the group and the warp class the columns are taken in MEMORY order (by first row), not
+    // by length: neighbouring warps then stream neighbouring rows, and DRAM pages are used whole
+    // (length order makes every column a random 1-2 KB access).  The classes themselves stay
+    // longest first, and the warp class is scheduled dynamically, so balance does not suffer.
+    {
+      std::vector<size_t> order(p0.items.size());
+      for (size_t k = 0; k < order.size(); k++)
+        order[k] = k;
+      const size_t g0 = static_cast<size_t>(f_nCC + f_nCR), w0 = g0 + f_nG;
+      auto by_row = [&](size_t x, size_t y) { return p0.items[x].lo < p0.items[y].lo; };
+      const char *keep = std::getenv("MYFM_FIELD_LENGTH_ORDER");
+      if (!(keep && keep[0] == '1')) {
+        std::sort(order.begin() + g0, order.begin() + w0, by_row);
+        std::sort(order.begin() + w0, order.end(), by_row);
+      }
+      std::vector<SweepItem> items(order.size());
+      std::vector<int> slots(order.size());
+      for (size_t k = 0; k < order.size(); k++)
+        items[k] = p0.items[order[k]], slots[k] = p0.item_slot[order[k]];
+      p0.items.swap(items), p0.item_slot.swap(slots);
+    }
     f_items0_host = p0.items, f_slot0_host = p0.item_slot;
     f_level_host = level;
     f_items0.upload(p0.items, stream);
