@@ -12,7 +12,8 @@ timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smok
 tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py --sweeps 2 > gpurun_out/ncu_launches.log 2>&1
+# launch list of the bench command itself (a number printed under ncu is never a bench value)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
 # full-set capture of the hot kernels; the report stays on the box, its raw page comes back as CSV
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_field_stream|k_field_stats|k_predict_tile" -s 40 -c 5 \
