@@ -577,7 +577,8 @@ template <typename Real> struct Trainer : TrainerBase {
       } else {
         if (world > 1)
           throw std::invalid_argument("row-sharded training needs column_level agreed between the ranks.");
-        level = compute_levels(Xth0, &n_levels);
+        if (!compute_levels_by_rows(Xh, level, &n_levels)) // rows with unsorted columns: serial, by column
+          level = compute_levels(Xth0, &n_levels);
       }
       tick("dependency levels");
       perm = primary_row_order(Xth0, level, n_levels, &primary);
@@ -2622,9 +2623,11 @@ int myfm_level_relax(const myfm_csr_t *X, int32_t *level, int32_t *n_levels, int
 int myfm_level_schedule(const myfm_csr_t *X, int32_t *level, int32_t *n_levels) {
   MYFM_API_BEGIN
   require(X, "X"), require(n_levels, "n_levels");
-  HostCs<float> Xt = host_transpose(host_from_api<float>(*X, "X"));
+  HostCs<float> Xh = host_from_api<float>(*X, "X");
   int nl = 0;
-  std::vector<int> lv = compute_levels(Xt, &nl);
+  std::vector<int> lv;
+  if (!compute_levels_by_rows(Xh, lv, &nl)) // what the trainer does: row-parallel when rows are sorted
+    lv = compute_levels(host_transpose(Xh), &nl);
   for (size_t j = 0; j < lv.size(); j++)
     level[j] = lv[j];
   *n_levels = nl;

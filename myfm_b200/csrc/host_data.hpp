@@ -152,14 +152,20 @@ template <typename Real> HostCs<Real> host_transpose(const HostCs<Real> &a) {
 // partial update; no parallel schedule can reproduce that, so such input is rejected (the Python
 // layer sums duplicates before calling).
 template <typename Real> bool has_duplicate_entries(const HostCs<Real> &csr) {
-  std::vector<int> seen(csr.n_minor, -1);
-  for (int64_t r = 0; r < csr.n_major; r++)
-    for (int p = csr.ptr[r]; p < csr.ptr[r + 1]; p++) {
-      if (seen[csr.idx[p]] == static_cast<int>(r))
-        return true;
-      seen[csr.idx[p]] = static_cast<int>(r);
-    }
-  return false;
+  std::atomic<bool> found{false};
+  parallel_parts(csr.n_minor > (1 << 22) ? 1 : parts_for(csr.nnz()), [&](int t, int np) {
+    auto [r0, r1] = part_range(csr.n_major, t, np);
+    std::vector<int> seen(csr.n_minor, -1); // last row that listed the column, per part
+    for (int64_t r = r0; r < r1 && !found.load(std::memory_order_relaxed); r++)
+      for (int p = csr.ptr[r]; p < csr.ptr[r + 1]; p++) {
+        if (seen[csr.idx[p]] == static_cast<int>(r)) {
+          found.store(true);
+          break;
+        }
+        seen[csr.idx[p]] = static_cast<int>(r);
+      }
+  });
+  return found.load();
 }
 
 // Dependency levels of the columns (given as the major axis of `csc`): the reference updates
@@ -185,6 +191,67 @@ std::vector<int> compute_levels(const HostCs<Real> &csc, int *n_levels_out,
   }
   *n_levels_out = n_levels;
   return level;
+}
+
+// The same schedule from the ROW side, on several threads.  Inside a row the entries in ascending
+// column order form a chain (each conflicts with its predecessor), and the level of a column is
+// one more than the highest level among its predecessors over all its rows — which is exactly the
+// serial recurrence above, because the last earlier column of a row already dominates the ones
+// before it.  The least fixed point is reached by relaxing all rows repeatedly (monotone, so the
+// order of the concurrent updates does not matter); the number of passes is the number of levels.
+// Needs every row's columns in ascending order: returns false (and leaves the output untouched)
+// when some row is not, the caller then takes compute_levels.
+template <typename Real>
+bool compute_levels_by_rows(const HostCs<Real> &csr, std::vector<int> &level_out, int *n_levels_out,
+                            const int *lower = nullptr) {
+  const int64_t n_rows = csr.n_major, n_cols = csr.n_minor;
+  const int n_parts = parts_for(csr.nnz());
+  std::atomic<bool> sorted{true};
+  parallel_parts(n_parts, [&](int t, int np) {
+    auto [r0, r1] = part_range(n_rows, t, np);
+    for (int64_t r = r0; r < r1 && sorted.load(std::memory_order_relaxed); r++)
+      for (int p = csr.ptr[r] + 1; p < csr.ptr[r + 1]; p++)
+        if (csr.idx[p] <= csr.idx[p - 1]) {
+          sorted.store(false);
+          break;
+        }
+  });
+  if (!sorted.load())
+    return false;
+  std::vector<std::atomic<int>> level(n_cols);
+  for (int64_t j = 0; j < n_cols; j++)
+    level[j].store(lower ? lower[j] : 0, std::memory_order_relaxed);
+  for (int pass = 0; pass <= n_cols; pass++) {
+    std::atomic<bool> changed{false};
+    parallel_parts(n_parts, [&](int t, int np) {
+      auto [r0, r1] = part_range(n_rows, t, np);
+      bool mine = false;
+      for (int64_t r = r0; r < r1; r++) {
+        int need = 0; // level the next entry of this row must reach at least
+        for (int p = csr.ptr[r]; p < csr.ptr[r + 1]; p++) {
+          std::atomic<int> &lv = level[csr.idx[p]];
+          int cur = lv.load(std::memory_order_relaxed);
+          while (cur < need && !lv.compare_exchange_weak(cur, need, std::memory_order_relaxed))
+            ;
+          if (cur < need)
+            mine = true, cur = need;
+          need = cur + 1;
+        }
+      }
+      if (mine)
+        changed.store(true);
+    });
+    if (!changed.load())
+      break;
+  }
+  level_out.resize(n_cols);
+  int n_levels = n_cols ? 1 : 0;
+  for (int64_t j = 0; j < n_cols; j++) {
+    level_out[j] = level[j].load(std::memory_order_relaxed);
+    n_levels = std::max(n_levels, level_out[j] + 1);
+  }
+  *n_levels_out = n_levels;
+  return true;
 }
 
 // Columns grouped by level.  Inside a level, columns longer than `long_threshold` come first

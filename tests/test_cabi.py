@@ -145,3 +145,40 @@ def test_host_transpose_threads(threads):
     np.testing.assert_array_equal(indptr, ref.indptr)
     np.testing.assert_array_equal(indices, ref.indices)
     np.testing.assert_array_equal(data, ref.data)
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_row_parallel_level_schedule_equals_serial(threads):
+    """compute_levels_by_rows (row side, several threads, what the trainer uses) against the serial
+    column-order recurrence (myfm_level_relax from all-zero lower bounds), on shapes with long
+    dependency chains; rows with unsorted columns take the serial route and give the same answer."""
+    from myfm_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    cases = [sps.random(3000, 120, 0.02, format="csr", random_state=1),
+             sps.random(500, 40, 0.3, format="csr", random_state=2),
+             movielens_like(4000, 90, 35, 2, seed=4)[0],
+             sps.csr_matrix(np.tril(np.ones((30, 30))))]
+    _lib.check(_lib.lib().myfm_set_host_threads(C.c_int32(threads)))
+    try:
+        for X in cases:
+            X = sps.csr_matrix(X)
+            X.sort_indices()
+            got, n = level_schedule(X)
+            h = _lib.CsrHolder(X)
+            serial = np.zeros(X.shape[1], dtype=np.int32)
+            nl, changed = C.c_int32(), C.c_int32()
+            _lib.check(_lib.lib().myfm_level_relax(C.byref(h.struct), _lib.vptr(serial), C.byref(nl), C.byref(changed)))
+            np.testing.assert_array_equal(got, serial)
+            assert n == nl.value
+            # the same matrix with every row's entries reversed (unsorted): serial fallback, same levels
+            Xr = X.copy()
+            for r in range(Xr.shape[0]):
+                lo, hi = Xr.indptr[r], Xr.indptr[r + 1]
+                Xr.indices[lo:hi] = Xr.indices[lo:hi][::-1].copy()
+                Xr.data[lo:hi] = Xr.data[lo:hi][::-1].copy()
+            Xr.has_sorted_indices = False
+            got_r, _ = level_schedule(Xr)
+            np.testing.assert_array_equal(got_r, serial)
+    finally:
+        _lib.check(_lib.lib().myfm_set_host_threads(C.c_int32(0)))

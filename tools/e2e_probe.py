@@ -11,7 +11,7 @@ X, y, gs, rank = bench.make_workload("ml10m")
 cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(gs)), gs)).set_n_iter(30)
        .set_n_kept_samples(1).build())
 t0 = time.perf_counter()
-with myfm_b200.engine_options(dtype="f32"):
+with myfm_b200.engine_options(dtype=os.environ.get("DTYPE", "f32")):
     t = _TrainerHandle(X, [], y, 42, cfg)
     t1 = time.perf_counter()
     t.init_fm(rank, 0.1)
