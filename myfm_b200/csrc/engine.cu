@@ -1401,8 +1401,6 @@ template <typename Real> struct Trainer : TrainerBase {
         const int warps = f_sm_count * FIELD_WARPS;
         int b = env ? std::atoi(env) : ceil_div(f_nW, 4 * static_cast<int64_t>(warps));
         a.batch = std::max(1, std::min(b, FIELD_BATCH_MAX));
-        const char *pf = std::getenv("MYFM_FIELD_PREFETCH");
-        a.prefetch = pf ? std::atoi(pf) : 0; // measured: no gain on B200 (the pass is issue-bound, not latency-bound)
       }
       a.eq = eq(), a.n_rows = N, a.n_tail = f_tail;
       a.tail_idx = f_tail_idx.p, a.tail_val = f_tail_val.p, a.own_val = f_own_val.p;

@@ -36,7 +36,6 @@ constexpr int STATS_CHUNK = 8192;     // one CTA per column up to here, chunks o
 
 enum { PEND_NONE = 0, PEND_W = 1, PEND_V = 2 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------
 // Row shards on one NVLink / NVSwitch node: the all-reduce of the column statistics is fused into
@@ -124,7 +123,6 @@ template <typename Real> struct FieldStreamArgs {
   const int4 *item; // level-0 columns {column, first row, end row, -}, longest first (classes: k_field_stream)
   int nCC, nCR, nG, nW;
   int batch;        // warp columns taken per scheduling step: 1 .. FIELD_BATCH_MAX (few columns: small batches)
-  int prefetch;     // pull the rows of a batch into L2 before its first column starts
   int *sched;       // work counter of the warp items (zero at launch)
   Pair<Real> *eq;
   int64_t n_rows;
@@ -518,8 +516,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   // handed out through a counter (one atomic per batch: same-address atomics retire at about one
   // per two cycles chip-wide, one per column would bound the kernel).  Lane b of the warp owns the
   // scalars of the batch's b-th column (item, theta, z, group hypers, and in FIELD_UPDATE its draw:
-  // one chain of dependent loads per BATCH, not per column), and the rows of the whole batch are
-  // pulled into L2 up front, so a column's own loads find their lines on chip.
+  // one chain of dependent loads per BATCH, not per column).
   const int total_warps = gridDim.x * FIELD_WARPS;
   const int first_w = a.nCC + a.nCR + a.nG;
   const int4 *items_w = a.item + first_w;
@@ -543,17 +540,6 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
         my_slot = a.item_slot[first_w + kb + lane];
       if (MODE == FIELD_UPDATE)
         my_given = draw_given(my_slot, my_theta, my_lam, my_mu, my_z);
-    }
-    for (int bi = 0; bi < (a.prefetch ? n_batch : 0); bi++) {
-      const int lo = __shfl_sync(FULL_MASK, my_it.y, bi), n = __shfl_sync(FULL_MASK, my_it.z, bi) - lo;
-      const char *p_eq = reinterpret_cast<const char *>(a.eq + lo);
-      for (int off = lane * 128; off < n * static_cast<int>(sizeof(Pair<Real>)); off += 32 * 128)
-        prefetch_l2(p_eq + off);
-      if (IS_V || PEND != PEND_NONE) {
-        const char *p_tail = reinterpret_cast<const char *>(a.tail_last + lo);
-        for (int off = lane * 128; off < n * 4; off += 32 * 128)
-          prefetch_l2(p_tail + off);
-      }
     }
     for (int bi = 0; bi < n_batch; bi++) {
       int4 it;
