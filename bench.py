@@ -4,6 +4,8 @@ MovieLens-10M-shaped workload (BASELINE.json configs[3]; SURVEY.md §8d config C
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA engine
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --workload ml1m-ext                      # C3: relation blocks (rank 16)
+    python bench.py --workload ml100k --task ordered         # probit / ordered-probit sweeps
 
 One JSON line on stdout (rank 0).  A "step" is one full update_all sweep (alpha, w0, hypers, w,
 K factor columns of V, e refresh) over the whole training set.
@@ -11,10 +13,11 @@ K factor columns of V, e refresh) over the whole training set.
 value     whole-job iterations/s, inputs resident in HBM, timed with CUDA events on the engine's
           stream around exactly K sweeps (barrier + synchronize on both sides, max over ranks).
 e2e       the same metric through the public API (MyFMRegressor.fit with host scipy/numpy
-          buffers): wall clock between the per-iteration callbacks, which includes every
-          host->device copy of the sweep's variates (pinned) and the device->host read of the
-          sweep's hyper-parameters.
+          buffers): wall clock between the per-iteration callbacks (steady state), and the whole
+          fit() including the one-off upload / data preparation (`including_setup`).
 roofline  column-sweep kernels (the dominant family): algorithmic bytes / CUDA-event time.
+At N > 1 the line also carries `parity_vs_1gpu`: the row-sharded chain against the 1-GPU chain on
+the same seed after the same number of sweeps.
 """
 from __future__ import annotations
 
@@ -37,31 +40,95 @@ WORKLOADS = {
     "ml10m": (10_000_054, 69_878, 10_677, 32),
     "ml1m": (900_188, 6_040, 3_706, 32),
     "ml100k": (80_000, 943, 1_682, 8),
+    # C3 (examples/ml-1m-extended.ipynb): day one-hot main table + user / movie relation blocks
+    # carrying the id one-hot and SVD++-style implicit features
+    "ml1m-ext": (900_188, 6_040, 3_706, 16),
 }
+ML1M_DAYS = 1_040
 DATA_SEED = 2
 CHAIN_SEED = 42
+N_CLASSES = 5
 
 
-def make_workload(name: str):
-    from helpers import movielens_like
+class Workload:
+    """Synthetic inputs of one configuration: main table, relation blocks (map, block), targets."""
 
-    rows, users, movies, rank = WORKLOADS[name]
-    # popularity exponents matched to ML-10M's public max/mean ratings per user (7359/143) and
-    # per movie (34864/937)
-    X, y, group_shapes = movielens_like(rows, users, movies, 8, seed=DATA_SEED, zipf=(0.4, 0.45))
-    y = np.clip(np.round(y * 2) / 2, 0.5, 5.0)  # half-star grid like ML-10M
-    return X, y, group_shapes, rank
+    def __init__(self, name: str, task: str = "regression", rank: int | None = None):
+        from helpers import ml1m_extended, movielens_like
 
+        rows, users, movies, default_rank = WORKLOADS[name]
+        self.name, self.task, self.rank = name, task, rank or default_rank
+        if name == "ml1m-ext":
+            X, ub, mb, y, gs = ml1m_extended(rows, users, movies, ML1M_DAYS, seed=DATA_SEED)
+            self.X, self.rel, self.group_shapes = X, [ub, mb], gs
+            y = np.clip(np.round(y), 1, 5)
+        else:
+            # popularity exponents matched to ML-10M's public max/mean ratings per user (7359/143)
+            # and per movie (34864/937)
+            X, y, gs = movielens_like(rows, users, movies, 8, seed=DATA_SEED, zipf=(0.4, 0.45))
+            self.X, self.rel, self.group_shapes = X, [], gs
+            y = np.clip(np.round(y * 2) / 2, 0.5, 5.0)  # half-star grid like ML-10M
+        if task == "classification":
+            y = (y > np.median(y)).astype(np.float64)  # 0 / 1 as MyFMClassifier takes it
+        elif task == "ordered":
+            y = np.clip(np.round(y), 1, N_CLASSES) - 1  # five ordinal classes 0 .. 4 (the star ratings)
+        self.y = y
+        self.nnz = int(X.nnz)
+        self.n_rows = int(X.shape[0])
 
-def algorithmic_bytes(nnz: int, n_rows: int, rank: int, real_bytes: int = 4):
-    """bytes one sweep must move (i32 indices, `real_bytes` values)."""
-    b = real_bytes
-    v_sweep = (4 + b) * nnz + 4 * b * nnz          # per factor: CSC read + gather/scatter of q, e
-    q_init = (4 + b) * nnz + 4 * n_rows + b * n_rows
-    w_sweep = (4 + b) * nnz + 2 * b * nnz
-    e_refresh = (4 + b) * nnz + 4 * n_rows + 2 * b * n_rows
-    misc = 3 * b * n_rows
-    return dict(sweeps=rank * v_sweep + w_sweep, total=rank * (v_sweep + q_init) + w_sweep + e_refresh + misc)
+    @property
+    def y_engine(self):
+        """Targets as the trainer takes them (classification: -1 / +1, src/myfm/base.py:385-386)."""
+        return self.y * 2 - 1 if self.task == "classification" else self.y
+
+    def description(self) -> str:
+        rows, users, movies, _ = WORKLOADS[self.name]
+        if self.name == "ml1m-ext":
+            nnz_b = [int(b.nnz) for _, b in self.rel]
+            shape = (f"{rows} rows x {ML1M_DAYS} day one-hot + user block {users} x {users + movies} (nnz {nnz_b[0]}) "
+                     f"+ movie block {movies} x {users + movies} (nnz {nnz_b[1]}), group_shapes={self.group_shapes}")
+        else:
+            shape = (f"{rows} rows x ({users} users + {movies} movies) one-hot, nnz={self.nnz}, "
+                     f"group_shapes=[users, movies]")
+        return f"{self.name}-shaped synthetic: {shape}, rank {self.rank}, {self.task}"
+
+    def config(self, n_iter: int):
+        from myfm_b200._myfm import ConfigBuilder, TaskType
+
+        b = (ConfigBuilder().set_mu_0(0.0)
+             .set_group_index(np.repeat(np.arange(len(self.group_shapes)), self.group_shapes))
+             .set_n_iter(n_iter).set_n_kept_samples(1))
+        b.set_task_type({"regression": TaskType.REGRESSION, "classification": TaskType.CLASSIFICATION,
+                         "ordered": TaskType.ORDERED}[self.task])
+        if self.task == "ordered":
+            b.set_cutpoint_groups([(int(self.y.max()) + 1, np.arange(self.n_rows))])
+        return b.build()
+
+    def blocks(self):
+        from myfm_b200._myfm import RelationBlock
+
+        return [RelationBlock(m, b) for m, b in self.rel]
+
+    def oracle_chain(self, dtype="f32"):
+        from oracle import binding as oracle
+
+        oracle.build()
+        return oracle.OracleChain(self.X, self.y_engine, self.rank, X_rel=list(self.rel), dtype=dtype,
+                                  task=self.task, seed=CHAIN_SEED, group_shapes=self.group_shapes, n_iter=10 ** 6)
+
+    def algorithmic_bytes(self, real_bytes: int = 4):
+        """bytes one sweep must move (i32 indices, `real_bytes` values)."""
+        b, nnz, n, K = real_bytes, self.nnz, self.n_rows, self.rank
+        v_sweep = (4 + b) * nnz + 4 * b * nnz          # per factor: CSC read + gather/scatter of q, e
+        q_init = (4 + b) * nnz + 4 * n + b * n
+        w_sweep = (4 + b) * nnz + 2 * b * nnz
+        e_refresh = (4 + b) * nnz + 4 * n + 2 * b * n
+        misc = 3 * b * n
+        # relation blocks (SURVEY §8d): per block per vector two passes over the row map with q, e
+        # read + write, and the block sweep itself
+        rel = sum((4 + 4 * b) * n * 2 + (4 + b) * int(B.nnz) for _, B in self.rel)
+        sweeps = K * (v_sweep + rel) + w_sweep + rel
+        return dict(sweeps=sweeps, total=sweeps + K * q_init + e_refresh + misc)
 
 
 class ClockSampler(threading.Thread):
@@ -99,16 +166,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def oracle_chain(X, y, group_shapes, rank, dtype="f32"):
-    from oracle import binding as oracle
-
-    oracle.build()
-    return oracle.OracleChain(X, y, rank, dtype=dtype, seed=CHAIN_SEED, group_shapes=group_shapes, n_iter=10 ** 6)
-
-
-def cpu_baseline(X, y, group_shapes, rank, budget_s: float = 20.0):
+def cpu_baseline(wl: Workload, budget_s: float = 20.0):
     """The reference's CPU path (oracle port, f32, 1 thread) on the same workload; bounded."""
-    chain = oracle_chain(X, y, group_shapes, rank)
+    chain = wl.oracle_chain()
     t1 = chain.timed_steps(1)  # warm-up, also sizes the sample
     n = int(max(1, min(20, budget_s // max(t1, 1e-3))))
     t = chain.timed_steps(n)
@@ -118,8 +178,12 @@ def cpu_baseline(X, y, group_shapes, rank, budget_s: float = 20.0):
                       f"{os.cpu_count()} cores)"}
 
 
+# DRAM bytes per launch of the column-sweep kernels from the newest committed `ncu --set full` capture
+SWEEP_KERNELS = ("k_field_stream", "k_field_stats", "k_tile_sweep", "k_tile_fold")
+
+
 def ncu_traffic(rank: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the two column-sweep kernels from the newest
+    """dram__bytes_read.sum + dram__bytes_write.sum of the column-sweep kernels from the newest
     committed `ncu --set full` capture (profiles/*_full_raw.csv), per sweep: (rank + 1) launches each."""
     import csv
     import glob
@@ -136,14 +200,23 @@ def ncu_traffic(rank: int):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     per_kernel = {}
     for r in rows[2:]:
-        for key in ("k_field_stream", "k_field_stats"):
+        for key in SWEEP_KERNELS:
             if key in r[i_name]:
                 b = float(r[i_rd]) * scale.get(units[i_rd], 1.0) + float(r[i_wr]) * scale.get(units[i_wr], 1.0)
                 per_kernel.setdefault(key, []).append(b)
-    if len(per_kernel) < 2:
+    if not per_kernel:
         return None, None
     per_vector = sum(sum(v) / len(v) for v in per_kernel.values())
-    return per_vector * (rank + 1), os.path.relpath(files[-1], ROOT)
+    return per_vector * (rank + 1), f"{os.path.relpath(files[-1], ROOT)} ({' + '.join(sorted(per_kernel))})"
+
+
+def base_config(wl: Workload, n_gpus: int, rng: str, parallelism: str):
+    return {"workload": wl.description(), "rank": wl.rank, "rows": wl.n_rows, "nnz": wl.nnz, "task": wl.task,
+            "rng": ("mt19937 (reference stream, same seed; generated on the device)" if rng == "mt19937" else
+                    "philox latent draws on the device (statistically equivalent chain); Gaussian / Gamma variates "
+                    "from the device-side mt19937 stream"),
+            "l2": "working set (CSR+CSC+{e,q},y) exceeds the 126 MB L2 for ml10m; no explicit flush",
+            "parallelism": parallelism}
 
 
 def run_reference(args):
@@ -152,8 +225,8 @@ def run_reference(args):
     rank_id = int(os.environ.get("RANK", "0"))
     if rank_id != 0:
         return
-    X, y, group_shapes, rank = make_workload(args.workload)
-    chain = oracle_chain(X, y, group_shapes, rank)
+    wl = Workload(args.workload, args.task, args.rank)
+    chain = wl.oracle_chain()
     # bounded: the full workload every step, but only as many steps as fit in ~3 minutes
     t1 = chain.timed_steps(1)
     budget = 180.0
@@ -168,8 +241,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
         "steps_run": steps, "warmup_run": 1 + warm,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, X.shape[0], X.nnz, rank, args.gpus),
-        "nnz_rank_per_sec": value * X.nnz * rank,
+        "config": base_config(wl, args.gpus, "mt19937", "CPU, 1 thread"),
+        "nnz_rank_per_sec": value * wl.nnz * wl.rank,
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": 1, "kind": "port",
                          "sample": f"{steps} full update_all sweeps (of {args.steps} asked; bounded to ~3 min) of the same "
                                    f"workload after {1 + warm} warm-up, oracle restatement of the reference sampler "
@@ -180,21 +253,48 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, n_rows, nnz, rank, n_gpus):
-    rows, users, movies, _ = WORKLOADS[name]
-    return {"workload": f"{name}-shaped synthetic: {rows} rows x ({users} users + {movies} movies) one-hot, "
-                        f"nnz={nnz}, rank {rank}, regression, group_shapes=[users, movies]",
-            "rank": rank, "rows": int(n_rows), "nnz": int(nnz),
-            "rng": "mt19937 (reference stream, same seed; generated on the device)",
-            "l2": "working set (CSR+CSC+{e,q},y ~ 0.5 GB) exceeds the 126 MB L2; no explicit flush",
-            "parallelism": "single GPU" if n_gpus == 1 else
-            f"rows sharded over {n_gpus} GPUs (contiguous ranges), one NCCL all-reduce of the column statistics "
-            f"per dependency level, model replicated"}
+# myfm_trainer_sweep_path -> what runs
+SWEEP_PATHS = {
+    0: ("general", "k_level_sweep + k_level_seg_update (dependency-level column sweeps, gather + scatter)"),
+    1: ("field", "k_field_stream + k_field_stats (column sweeps of w and of the K factor columns: streaming level "
+                 "with fused q_init, gather-only last level)"),
+    2: ("field+peer", "k_field_stream<STATS/UPDATE> + k_field_stats + k_field_draw_last, column statistics "
+                      "exchanged through peer memory inside the kernels"),
+    3: ("field-exclusive+nccl", "k_field_stream (rank-exclusive first field: no exchange) + k_field_stats + "
+                                "ncclAllReduce + k_field_draw_last"),
+    4: ("field-exclusive+peer", "k_field_stream (rank-exclusive first field: no exchange) + k_field_stats + "
+                                "k_field_draw_last reading the peers' statistics over NVLink"),
+    5: ("tile", "k_tile_sweep + k_tile_fold (row tiles staged in shared memory by TMA bulk copies: pending update, "
+                "first-field sweep and last-field statistics in one pass)"),
+    6: ("tile+peer", "k_tile_sweep + k_tile_fold (rank-exclusive row tiles; per-column statistics of the last "
+                     "field exchanged through peer memory)"),
+}
+
+
+def parallelism_label(n_gpus: int, sweep_path: int, partition: str) -> str:
+    if n_gpus == 1:
+        return "single GPU"
+    how = {0: "one ncclAllReduce of the column statistics per dependency level",
+           1: "ncclAllReduce of the column statistics per level (field path)",
+           2: "column statistics of both levels exchanged through peer memory (NVLink) inside the sweep kernels",
+           3: "first field rank-exclusive (no exchange), last field: ncclAllReduce of its column statistics per vector",
+           4: "first field rank-exclusive (no exchange), last field: column statistics read from the peers over "
+              "NVLink inside the draw kernel, one exchange per vector",
+           6: "row tiles rank-exclusive by first field; last field: per-column statistics read from the peers over "
+              "NVLink, one exchange per vector"}.get(sweep_path, "?")
+    return (f"rows sharded over {n_gpus} GPUs (partition='{partition}': rows dealt out by their first-field column), "
+            f"model replicated; {how}")
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(float(np.max(np.abs(b))), 1e-30)
+    return float(np.max(np.abs(a - b)) / scale)
 
 
 def run_ours(args):
     import myfm_b200
-    from myfm_b200._myfm import ConfigBuilder, _TrainerHandle
+    from myfm_b200._myfm import _TrainerHandle
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank_id = int(os.environ.get("RANK", "0"))
@@ -208,22 +308,26 @@ def run_ours(args):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
 
-    X, y, group_shapes, rank = make_workload(args.workload)
-    n_rows_global, nnz_global = X.shape[0], X.nnz
+    wl = Workload(args.workload, args.task, args.rank)
+    rank = wl.rank
+    X, y = wl.X, wl.y_engine
     dtype = args.dtype
-    cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(group_shapes)), group_shapes))
-           .set_n_iter(args.steps + args.warmup).set_n_kept_samples(1).build())
-    if dist is not None:  # every rank generated the same data; keep this rank's contiguous row range
+    n_total = args.steps + args.warmup
+    cfg = wl.config(n_total)
+    partition = "column"
+    if dist is not None:  # every rank generated the same data; keep this rank's rows
+        if wl.rel:
+            raise SystemExit("relation blocks are single-GPU (the blocks' row caches are not sharded yet)")
         from myfm_b200 import distributed as mdist
 
-        X, y, ctx = mdist.shard(X, y)
-        options = lambda: ctx.options(dtype=dtype, device=local)  # noqa: E731
+        X, y, ctx = mdist.shard(X, y, partition=partition)
+        options = lambda: ctx.options(dtype=dtype, device=local, rng=args.rng)  # noqa: E731
     else:
-        options = lambda: myfm_b200.engine_options(dtype=dtype, device=local)  # noqa: E731
+        options = lambda: myfm_b200.engine_options(dtype=dtype, device=local, rng=args.rng)  # noqa: E731
 
     # ---- device-resident leg ---------------------------------------------------------------
     with options():
-        trainer = _TrainerHandle(X, [], y, CHAIN_SEED, cfg)
+        trainer = _TrainerHandle(X, wl.blocks(), y, CHAIN_SEED, cfg)
         trainer.init_fm(rank, 0.1)
     trainer.step(args.warmup)
     trainer.sync()
@@ -255,9 +359,38 @@ def run_ours(args):
     sweep_path = trainer.sweep_path()
     del trainer
 
+    # ---- N > 1: the sharded chain against the 1-GPU chain, same seed, same number of sweeps ----
+    parity = None
+    if dist is not None:
+        n_par = 3
+        with options():
+            tp = _TrainerHandle(X, [], y, CHAIN_SEED, cfg)
+            tp.init_fm(rank, 0.1)
+        tp.step(n_par)
+        tp.sync()
+        w0s, ws, Vs, _ = tp.get_fm()
+        hs = tp.get_hyper()
+        del tp
+        dist.barrier()
+        if rank_id == 0:
+            with myfm_b200.engine_options(dtype=dtype, device=local, rng=args.rng):
+                t1 = _TrainerHandle(wl.X, [], wl.y_engine, CHAIN_SEED, cfg)
+                t1.init_fm(rank, 0.1)
+            t1.step(n_par)
+            t1.sync()
+            w01, w1, V1, _ = t1.get_fm()
+            h1 = t1.get_hyper()
+            del t1
+            parity = {"sweeps": n_par, "max_rel_w": rel_err(ws, w1), "max_rel_V": rel_err(Vs, V1),
+                      "rel_w0": abs(w0s - w01) / max(abs(w01), 1e-30), "rel_alpha": abs(hs.alpha - h1.alpha) / h1.alpha,
+                      "alpha_equal": bool(hs.alpha == h1.alpha),
+                      "note": "max |sharded - single| / max |single| per array after `sweeps` sweeps from the same seed "
+                              f"({dtype}: the cross-rank sums add the same numbers in another order)"}
+        dist.barrier()
+
     it_per_s = args.steps / (ms / 1e3)
     real_bytes = 4 if dtype == "f32" else 8
-    bytes_ = algorithmic_bytes(X.nnz, X.shape[0], rank, real_bytes)
+    bytes_ = wl.algorithmic_bytes(real_bytes)
 
     # ---- end-to-end leg: the call a user makes --------------------------------------------------
     stamps = []
@@ -271,26 +404,39 @@ def run_ours(args):
         dist.barrier()
     t_fit0 = time.perf_counter()
     with options():
-        model = myfm_b200.MyFMRegressor(rank=rank, random_seed=CHAIN_SEED)
-        model.fit(X, y, n_iter=args.steps + args.warmup, n_kept_samples=1, group_shapes=group_shapes,
+        if wl.task == "regression":
+            model = myfm_b200.MyFMRegressor(rank=rank, random_seed=CHAIN_SEED)
+        elif wl.task == "classification":
+            model = myfm_b200.MyFMClassifier(rank=rank, random_seed=CHAIN_SEED)
+        else:
+            model = myfm_b200.MyFMOrderedProbit(rank=rank, random_seed=CHAIN_SEED)
+        # sharded runs hand fit() this rank's rows; targets in the estimator's own convention
+        y_fit = wl.y if dist is None else np.asarray(wl.y)[ctx.rows]
+        model.fit(X, y_fit, X_rel=wl.blocks(), n_iter=n_total, n_kept_samples=1, group_shapes=wl.group_shapes,
                   callback=callback)
     t_fit = time.perf_counter() - t_fit0
     e2e_s = stamps[-1] - stamps[args.warmup - 1] if args.warmup > 0 else stamps[-1] - t_fit0
+    setup_s = stamps[0] - t_fit0  # everything before the first sweep's callback, minus one sweep below
     if dist is not None:
         import torch
 
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([e2e_s, t_fit, setup_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, t_fit, setup_s = (float(v) for v in t.tolist())
     e2e = args.steps / e2e_s
-    G = len(group_shapes)
+    setup_s = max(0.0, setup_s - e2e_s / args.steps)
+    G = len(wl.group_shapes)
     # Host->device: a Gibbs fit uploads its inputs (X as CSR with int64 indptr / int32 indices / f64 values, y)
     # once, inside fit(); the sweeps read nothing else from the host (the variates come from the device-side
     # mt19937).  Reported amortised over the sweeps of this fit.  Device->host per sweep: the sweep's
     # hyper-parameters (LearningHistory) and the bias the callback reads.
     upload = X.indptr.shape[0] * 8 + X.nnz * (4 + 8) + y.shape[0] * 8
-    h2d = upload / (args.steps + args.warmup)
+    upload += sum(B.indptr.shape[0] * 8 + B.nnz * 12 + np.asarray(m).shape[0] * 8 for m, B in wl.rel)
+    h2d = upload / n_total
     d2h = (2 + 2 * G + 2 * G * rank) * real_bytes + real_bytes
+    if wl.task != "regression" and args.rng == "mt19937":  # the latent draws run on the host: e both ways
+        h2d += X.shape[0] * real_bytes
+        d2h += X.shape[0] * real_bytes
 
     if rank_id != 0:
         dist.destroy_process_group()
@@ -301,33 +447,38 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = bytes_["sweeps"] * args.steps / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else None
-    traffic, traffic_src = ncu_traffic(rank) if (sweep_path >= 1 and args.gpus == 1 and args.workload == "ml10m"
+    traffic, traffic_src = ncu_traffic(rank) if (sweep_path in (1, 5) and args.gpus == 1 and args.workload == "ml10m"
                                                  and dtype == "f32") else (None, None)
+    path_name, kernel_desc = SWEEP_PATHS.get(sweep_path, (str(sweep_path), "?"))
+    config_n_iter = 200  # the iteration count BASELINE.json's C4 is quoted on
     line = {
         "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": workload_config(args.workload, n_rows_global, nnz_global, rank, args.gpus),
-        "nnz_rank_per_sec": it_per_s * nnz_global * rank,
+        "config": base_config(wl, args.gpus, args.rng, parallelism_label(args.gpus, sweep_path, partition)),
+        "sweep_path": path_name,
+        "nnz_rank_per_sec": it_per_s * wl.nnz * rank,
         "e2e": {"value": e2e, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "fit_total_s": t_fit, "fit_it_per_s_including_setup": (args.steps + args.warmup) / t_fit,
-                "note": "MyFMRegressor.fit() with host scipy/numpy buffers; wall clock between per-iteration callbacks "
-                        "(each reads the sweep's hyper-parameters and bias from the device).  The one-off input upload "
-                        "(h2d_bytes_per_step = upload bytes / sweeps of this fit), transpose and level schedule are "
-                        "inside fit_total_s"},
+                "fit_total_s": t_fit, "setup_s": setup_s,
+                "including_setup": {"it_per_s_this_fit": n_total / t_fit, "n_iter_this_fit": n_total,
+                                    "it_per_s_at_config_n_iter": config_n_iter / (setup_s + config_n_iter / e2e),
+                                    "config_n_iter": config_n_iter},
+                "note": "value: MyFM*.fit() with host scipy/numpy buffers, wall clock between per-iteration callbacks "
+                        "(each reads the sweep's hyper-parameters and bias from the device), steady state.  "
+                        "including_setup: the whole fit() with its one-off input upload (h2d_bytes_per_step = upload "
+                        "bytes / sweeps of this fit), transposes, level schedule; measured for this fit's n_iter and "
+                        "projected (setup_s + n / value) to the configuration's own n_iter"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "traffic_source": (f"{traffic_src}: dram read+write of k_field_stream + k_field_stats per launch x "
-                                        f"{rank + 1} vectors per sweep (bytes per step, like algorithmic_bytes_per_step)")
-                     if traffic else None, "peak_source": peak_src,
-                     "kernel": ("k_field_stream + k_field_stats (column sweeps of w and of the K factor columns: "
-                                "streaming level with fused q_init, gather-only last level)" if sweep_path == 1 else
-                                "k_level_sweep + k_level_seg_update (column sweeps of w and of the K factor columns"
-                                + ("; k_level_dist on this rank's row shard" if args.gpus > 1 else "") + ")"),
+                     "traffic_source": (f"{traffic_src}: dram read+write per launch x {rank + 1} vectors per sweep "
+                                        f"(bytes per step, like algorithmic_bytes_per_step)") if traffic else None,
+                     "peak_source": peak_src, "kernel": kernel_desc,
                      "algorithmic_bytes_per_step": bytes_["sweeps"], "launch_groups": int(sweep_launches),
                      "share_of_step": sweep_ms / ms_profiled if ms_profiled else None,
+                     "frac_of_measured_traffic": (traffic * args.steps / (sweep_ms / 1e3) / 1e9 / peak)
+                     if traffic and sweep_ms > 0 else None,
                      "whole_step_GBps": bytes_["total"] * it_per_s / 1e9,
                      "whole_step_frac": bytes_["total"] * it_per_s / 1e9 / peak},
         "kernel_ms_per_step": {"column_sweeps": sweep_ms / args.steps, "q_init": qinit_ms / args.steps,
@@ -336,8 +487,10 @@ def run_ours(args):
                                "step_while_profiled": ms_profiled / args.steps},
         "alpha_last": hyper.alpha,
     }
+    if parity is not None:
+        line["parity_vs_1gpu"] = parity
     if args.gpus == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(X, y, group_shapes, rank)
+        line["cpu_baseline"] = cpu_baseline(wl)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -350,6 +503,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--task", default="regression", choices=["regression", "classification", "ordered"])
+    ap.add_argument("--rank", type=int, default=None, help="override the workload's rank")
+    ap.add_argument("--rng", default="mt19937", choices=["mt19937", "philox"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -358,6 +514,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+
+
+def make_workload(name: str):
+    """(X, y, group_shapes, rank) of a two-field workload (tests and tools use this)."""
+    wl = Workload(name)
+    return wl.X, wl.y, wl.group_shapes, wl.rank
 
 
 if __name__ == "__main__":

@@ -245,6 +245,12 @@ int myfm_level_relax(const myfm_csr_t *X, int32_t *level, int32_t *n_levels, int
  * myfm_set_host_threads: number of threads the preparation passes use (0 = default). */
 int myfm_host_transpose(const myfm_csr_t *X, int64_t *indptr_out, int32_t *indices_out, double *data_out);
 int myfm_set_host_threads(int32_t n);
+/* Jump-ahead polynomial of std::mt19937 used by the parallel device generator (csrc/mt_jump.hpp,
+ * csrc/mt_device.cuh: k_mt_farm): the exponents i with g_i = 1 of g = t^n mod phi, phi the
+ * characteristic polynomial of MT19937, so that out[a + n + j] = XOR_i out[a + i + j] for the
+ * generator's output words.  Writes their number to *n_taps and, when capacity suffices, the
+ * exponents (ascending) to taps_out. */
+int myfm_mt_jump_taps(uint64_t n, uint16_t *taps_out, int32_t capacity, int32_t *n_taps);
 /* ncclGetUniqueId for the row-sharded trainer: rank 0 calls it and ships the 128 bytes to the
  * other ranks by any side channel (myfm_b200/distributed.py uses torch.distributed). */
 int myfm_nccl_unique_id(void *out128);

@@ -94,6 +94,7 @@ EXPORTS = [
     "myfm_predict_oprobit_mean", "myfm_trainer_predict_score", "myfm_rng_fill",
     "myfm_trainer_snapshot", "myfm_sample_destroy", "myfm_sample_get", "myfm_predict_samples_mean",
     "myfm_level_schedule", "myfm_level_relax", "myfm_host_transpose", "myfm_set_host_threads", "myfm_nccl_unique_id",
+    "myfm_mt_jump_taps",
 ]
 
 _lib: Optional[C.CDLL] = None

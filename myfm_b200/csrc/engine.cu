@@ -9,6 +9,7 @@
 #include "field_sweep.cuh"
 #include "latent_device.cuh"
 #include "mt_device.cuh"
+#include "mt_jump.hpp"
 #include "oprobit.cuh"
 #include "rng.hpp"
 
@@ -852,12 +853,36 @@ template <typename Real> struct Trainer : TrainerBase {
     const long long need = (bulk_attempts(D_all) + bulk_attempts(static_cast<long long>(K) * D_all)) * WPA +
                            64 * n_scalar + MT_SCALAR_WINDOW;
     mt_ahead = static_cast<unsigned long long>(need);
+    // Large sweeps: the word stream comes from MT_FARM_LANES lanes at once (k_mt_farm), one block of
+    // lanes x seg words per sweep; small ones keep the single serial CTA (its 100 ns per 227 words
+    // are hidden behind the sweep anyway).  MYFM_MT_FARM="lanes,seg" forces a shape (tests).
+    mt_farm_lanes = 0, mt_farm_seg = 0;
+    {
+      const char *env = std::getenv("MYFM_MT_FARM");
+      long long lanes = 0, seg = 0;
+      if (env && std::sscanf(env, "%lld,%lld", &lanes, &seg) == 2) {
+        if (lanes > 1 && seg > MT_JUMP_SPAN)
+          mt_farm_lanes = static_cast<int>(lanes), mt_farm_seg = static_cast<unsigned long long>(seg);
+      } else if (need >= (1ll << 20)) {
+        mt_farm_lanes = MT_FARM_LANES;
+        mt_farm_seg = static_cast<unsigned long long>(ceil_div(ceil_div(need, MT_FARM_LANES), MT_LAG)) * MT_LAG;
+      }
+    }
+    const unsigned long long farm_block = mt_farm_seg * static_cast<unsigned long long>(mt_farm_lanes);
     unsigned long long cap = 1 << 16;
-    while (cap < 2 * mt_ahead + 4 * MT_N)
+    while (cap < 2 * mt_ahead + 4 * MT_N || cap < 3 * farm_block + mt_ahead + 4 * MT_N)
       cap <<= 1;
     mt_mask = cap - 1;
     mt_ring.alloc(cap);
     mt_ring.upload(first_words.data(), MT_N, stream);
+    if (mt_farm_lanes) {
+      const std::vector<uint16_t> &taps =
+          mt_jump_taps(farm_block - mt_farm_seg + static_cast<unsigned long long>(MT_JUMP_SPAN));
+      mt_farm_taps.upload(taps, stream);
+      mt_farm_n_taps = static_cast<int>(taps.size());
+      std::vector<unsigned long long> blocks(mt_farm_lanes, 1ull); // block 0 comes from k_mt_generate
+      mt_farm_blocks.upload(blocks, stream);
+    }
     // stages of a sweep: head scalars, w bulk, V-hyper scalars, V bulk (absent ones are skipped)
     mt_final_stage = 1 + (layout.z_w >= 0 && D_all > 0 ? 1 : 0) + (G > 0 && K > 0 ? 1 : 0) +
                      (K > 0 && D_all > 0 ? 1 : 0);
@@ -876,7 +901,22 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     mt_consts.upload(consts, stream);
     MYFM_CUDA(cudaStreamSynchronize(stream));
+    if (mt_farm_lanes) { // block 0 of the farm: the serial generator, once
+      k_mt_generate<<<1, MT_GEN_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, farm_block - p,
+                                                           mt_final_stage);
+      launched();
+      const size_t smem = mt_farm_n_taps * sizeof(uint16_t);
+      MYFM_CUDA(cudaFuncSetAttribute(k_mt_farm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
+      MYFM_CUDA(cudaGetLastError());
+    }
   }
+  static constexpr int MT_FARM_LANES = 32;
+  int mt_farm_lanes = 0;                  // 0: serial generator (k_mt_generate) every sweep
+  unsigned long long mt_farm_seg = 0;     // words per lane per block
+  DevBuf<uint16_t> mt_farm_taps;
+  int mt_farm_n_taps = 0;
+  DevBuf<unsigned long long> mt_farm_blocks;
 
   // polar attempts examined for `count` bulk normals (mt_device.cuh)
   static long long bulk_attempts(long long count) {
@@ -907,7 +947,16 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaStreamWaitEvent(rng_stream, z_free[slot], 0));
     const SweepLayout &L = layout;
     Real *out = z_slot[slot].p;
-    k_mt_generate<<<1, MT_GEN_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, mt_ahead, mt_final_stage);
+    if (mt_farm_lanes) {
+      MtFarm farm;
+      farm.lanes = mt_farm_lanes, farm.seg = mt_farm_seg;
+      farm.n_taps = mt_farm_n_taps, farm.taps = mt_farm_taps.p;
+      farm.lane_blocks = mt_farm_blocks.p;
+      k_mt_farm<<<mt_farm_lanes, MT_FARM_THREADS, mt_farm_n_taps * sizeof(uint16_t), rng_stream>>>(
+          mt_ctl.p, mt_ring.p, mt_mask, mt_ahead, mt_final_stage, farm);
+    } else {
+      k_mt_generate<<<1, MT_GEN_THREADS, 0, rng_stream>>>(mt_ctl.p, mt_ring.p, mt_mask, mt_ahead, mt_final_stage);
+    }
     launched();
     int stage = 0;
     { // alpha, w0, lambda_w, mu_w
@@ -2586,6 +2635,16 @@ int myfm_host_transpose(const myfm_csr_t *X, int64_t *indptr_out, int32_t *indic
 int myfm_set_host_threads(int32_t n) {
   MYFM_API_BEGIN
   host_threads_override().store(n > 0 ? n : 0);
+  MYFM_API_END
+}
+
+int myfm_mt_jump_taps(uint64_t n, uint16_t *taps_out, int32_t capacity, int32_t *n_taps) {
+  MYFM_API_BEGIN
+  require(n_taps, "n_taps");
+  const std::vector<uint16_t> &taps = mt_jump_taps(n);
+  *n_taps = static_cast<int32_t>(taps.size());
+  if (taps_out && capacity >= *n_taps)
+    std::memcpy(taps_out, taps.data(), taps.size() * sizeof(uint16_t));
   MYFM_API_END
 }
 

@@ -136,6 +136,106 @@ __global__ void __launch_bounds__(MT_GEN_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same stream from P lanes at once (one CTA each).  The stream is cut into blocks of P * J
+// words; lane k produces words [b P J + k J, b P J + (k + 1) J) of block b.  A lane reaches its next
+// segment by JUMPING over the (P - 1) J words the other lanes produce: MT19937 is linear over
+// GF(2), so with g = t^(Jtot) mod phi (mt_jump.hpp; Jtot = (P - 1) J + MT_JUMP_SPAN) the first 624
+// words of the new segment are
+//     x[start + j] = XOR over the taps i of g of x[start - Jtot + i + j],      j = 0 .. 623,
+// a data-parallel XOR reduction over the last 19937 + 623 words of the lane's previous segment,
+// which still lie in the ring (tempering is a linear bijection per word, so the tempered ring words
+// are combined and the result is untempered for the recurrence).  The other J - 624 words of the
+// segment follow from the recurrence as in k_mt_generate.  Block 0 comes from k_mt_generate (the
+// host hands over one state, not P), every later block from this kernel; no lane ever waits for
+// another one.  Bit-identical to the serial stream by construction; the parity tests compare it
+// with libstdc++ draw for draw.
+// ------------------------------------------------------------------------------------------------
+constexpr int MT_FARM_THREADS = 640;   // 624 outputs of a jump, 227 words of a round
+constexpr int MT_JUMP_SPAN_DEV = 19937 + 623;
+
+struct MtFarm {
+  int lanes;                        // P
+  unsigned long long seg;           // J, at least MT_JUMP_SPAN_DEV + 1
+  int n_taps;
+  const unsigned short *taps;       // exponents of g, ascending
+  unsigned long long *lane_blocks;  // [P] blocks every lane has completed (block 0: k_mt_generate)
+};
+
+__host__ __device__ __forceinline__ uint32_t mt_untemper(uint32_t z) {
+  z ^= z >> 18;
+  z ^= (z << 15) & 0xefc60000u;
+  uint32_t t = z; // z = t ^ ((t << 7) & mask): recover 7 bits per step
+  for (int i = 0; i < 4; i++)
+    t = z ^ ((t << 7) & 0x9d2c5680u);
+  z = t;
+  t = z; // z = t ^ (t >> 11)
+  t = z ^ (t >> 11);
+  t = z ^ (t >> 11);
+  return t;
+}
+
+__global__ void __launch_bounds__(MT_FARM_THREADS)
+    k_mt_farm(MtControl *ctl, uint32_t *ring, unsigned long long mask, unsigned long long ahead, int final_stage,
+              MtFarm f) {
+  extern __shared__ __align__(8) unsigned short s_taps[];
+  __shared__ uint32_t W[MT_WINDOW];
+  const int t = threadIdx.x, lane_id = blockIdx.x;
+  const unsigned long long consumed = ctl->pos[final_stage];
+  const unsigned long long block_words = f.seg * static_cast<unsigned long long>(f.lanes);
+  const unsigned long long target = (consumed + ahead + block_words - 1) / block_words; // blocks that must exist
+  unsigned long long b = f.lane_blocks[lane_id];
+  if (b < target)
+    for (int i = t; i < f.n_taps; i += MT_FARM_THREADS)
+      s_taps[i] = f.taps[i];
+  __syncthreads();
+  for (; b < target; b++) {
+    const unsigned long long start = b * block_words + lane_id * f.seg;
+    const unsigned long long src = start - (block_words - f.seg) - MT_JUMP_SPAN_DEV;
+    if (t < MT_N) {
+      uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+      const unsigned long long base = src + t;
+      int i = 0;
+      for (; i + 4 <= f.n_taps; i += 4) { // four independent loads in flight
+        const ushort4 tp = *reinterpret_cast<const ushort4 *>(s_taps + i);
+        acc0 ^= ring[(base + tp.x) & mask];
+        acc1 ^= ring[(base + tp.y) & mask];
+        acc2 ^= ring[(base + tp.z) & mask];
+        acc3 ^= ring[(base + tp.w) & mask];
+      }
+      for (; i < f.n_taps; i++)
+        acc0 ^= ring[(base + s_taps[i]) & mask];
+      const uint32_t tempered = (acc0 ^ acc1) ^ (acc2 ^ acc3);
+      ring[(start + t) & mask] = tempered;
+      W[(start + t) & (MT_WINDOW - 1)] = mt_untemper(tempered);
+    }
+    __syncthreads();
+    unsigned long long m = start + MT_N;
+    const unsigned long long end = start + f.seg;
+    uint32_t prev = 0;
+    if (t < MT_LAG)
+      prev = W[(m + t - MT_LAG) & (MT_WINDOW - 1)];
+    while (m < end) { // as k_mt_generate; the last round of a segment may be partial
+      if (t < MT_LAG && m + t < end) {
+        const unsigned long long n = m + t;
+        const uint32_t v = prev ^ mt_twist(W[(n - MT_N) & (MT_WINDOW - 1)], W[(n - MT_N + 1) & (MT_WINDOW - 1)]);
+        W[n & (MT_WINDOW - 1)] = v;
+        ring[n & mask] = mt_temper(v);
+        prev = v;
+      }
+      m += MT_LAG;
+      __syncthreads();
+    }
+  }
+  if (t == 0) {
+    f.lane_blocks[lane_id] = b;
+    if (lane_id == 0) {
+      ctl->pos[0] = consumed; // the next sweep starts where the last one stopped
+      ctl->produced = target * block_words;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Scalar draws.  One CTA; thread 0 interprets the stream out of a shared-memory window of the
 // ring that all threads refill between draws (words beyond the window are read from the ring
 // directly: a draw that needs more than MT_SCALAR_RESERVE words has probability < 1e-30).

@@ -158,3 +158,21 @@ def fields_like(n_rows: int, field_sizes, rank: int, seed: int, unit: bool = Tru
     X2.data = X2.data ** 2
     y = 1.0 + X.dot(w) + 0.5 * ((X.dot(F.T) ** 2).sum(1) - X2.dot((F ** 2).sum(0))) + rng.normal(0, noise, n_rows)
     return X, y, list(field_sizes)
+
+
+def ml1m_extended(n_rows, n_users, n_movies, n_days, seed):
+    """Main table: day one-hot; user block: id one-hot + implicit feedback (movies rated, 1/sqrt n);
+    movie block: id one-hot + implicit (users who rated it)."""
+    rng = np.random.default_rng(seed)
+    users = rng.integers(0, n_users, n_rows)
+    movies = rng.integers(0, n_movies, n_rows)
+    days = rng.integers(0, n_days, n_rows)
+    R = sps.csr_matrix((np.ones(n_rows), (users, movies)), shape=(n_users, n_movies))
+    R.data[:] = 1.0
+    Ru = sps.diags(1.0 / np.sqrt(np.maximum(1, np.asarray(R.sum(1)).ravel()))) @ R
+    Rm = sps.diags(1.0 / np.sqrt(np.maximum(1, np.asarray(R.sum(0)).ravel()))) @ R.T
+    user_block = sps.hstack([sps.eye(n_users), Ru]).tocsr()
+    movie_block = sps.hstack([sps.eye(n_movies), Rm]).tocsr()
+    main = sps.csr_matrix((np.ones(n_rows), (np.arange(n_rows), days)), shape=(n_rows, n_days))
+    y = 3.5 + rng.normal(0, 0.3, n_users)[users] + rng.normal(0, 0.3, n_movies)[movies] + rng.normal(0, 0.9, n_rows)
+    return main, (users, user_block), (movies, movie_block), y, [n_days, n_users, n_movies, n_movies, n_users]

@@ -182,3 +182,31 @@ def test_row_parallel_level_schedule_equals_serial(threads):
             np.testing.assert_array_equal(got_r, serial)
     finally:
         _lib.check(_lib.lib().myfm_set_host_threads(C.c_int32(0)))
+
+
+@pytest.mark.parametrize("n", [20561, 31 * 32915 + 20560, (1 << 33) + 12345])
+def test_mt19937_jump_polynomial(n):
+    """csrc/mt_jump.hpp: g = t^n mod phi(MT19937).  The generator's output words satisfy
+    out[a + n + j] = XOR over the taps i of g of out[a + i + j]; checked against numpy's MT19937
+    (the same generator as std::mt19937: identical tempered 32-bit outputs).  The device generator's
+    lanes (mt_device.cuh: k_mt_farm) reach their next segment with exactly this identity."""
+    from myfm_b200 import _lib
+
+    count = C.c_int32()
+    _lib.check(_lib.lib().myfm_mt_jump_taps(C.c_uint64(n), None, C.c_int32(0), C.byref(count)))
+    taps = np.zeros(count.value, dtype=np.uint16)
+    _lib.check(_lib.lib().myfm_mt_jump_taps(C.c_uint64(n), _lib.vptr(taps), C.c_int32(taps.shape[0]), C.byref(count)))
+    assert 9000 < taps.shape[0] < 11000 or n < 30000  # about half of the 19937 coefficients
+    assert np.all(np.diff(taps.astype(np.int64)) > 0) and int(taps[-1]) < 19937
+    if n > (1 << 26):
+        return  # too far to walk on the CPU; the polynomial arithmetic is the same code path
+    bitgen = np.random.MT19937(5489)
+    # std::mt19937(seed) and numpy's legacy seeding agree for init_genrand
+    bitgen._legacy_seeding(5489)
+    span = 19937 + 623
+    words = bitgen.random_raw(n + span + 700).astype(np.uint32)
+    for a in (1, 5, 333):
+        acc = np.zeros(624, dtype=np.uint32)
+        for i in taps.astype(np.int64):
+            acc ^= words[a + i:a + i + 624]
+        np.testing.assert_array_equal(acc, words[a + n:a + n + 624])

@@ -2,7 +2,8 @@
 API / C ABI against the oracle on the same seed:
 
 C2  ML-100k-shaped, rank 8: held-out RMSE of the two predictors agrees to 1e-5
-C3  ML-1M-extended-shaped (relation blocks with implicit-feedback features), rank 16, reduced rows
+C3  ML-1M-extended-shaped (relation blocks with implicit-feedback features), rank 16: reduced rows
+    (4 sweeps) and at the full block size of the configuration (2 sweeps)
 C4  ML-10M-shaped at FULL size, rank 32, f32: two sweeps against the oracle (1e-4), plus
     size-independent properties: the residual cache equals prediction - y, runs are bit-reproducible
 C5  64 categorical fields, ordered probit (reduced rows): 64 dependency levels, of which 62 run the
@@ -12,7 +13,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sps
 
-from helpers import fields_like, movielens_like
+from helpers import fields_like, ml1m_extended, movielens_like
 from test_gpu_parity import assert_state_close, close, make_pair, run_chain_parity
 
 pytestmark = pytest.mark.gpu
@@ -39,28 +40,27 @@ def test_c2_heldout_rmse_matches_oracle(engine, oracle):
         assert rmse[0] < 1.2  # and the model actually learned something (planted noise 0.9)
 
 
-def _ml1m_extended(n_rows, n_users, n_movies, n_days, seed):
-    """Main table: day one-hot; user block: id one-hot + implicit feedback (movies rated, 1/sqrt n);
-    movie block: id one-hot + implicit (users who rated it)."""
-    rng = np.random.default_rng(seed)
-    users = rng.integers(0, n_users, n_rows)
-    movies = rng.integers(0, n_movies, n_rows)
-    days = rng.integers(0, n_days, n_rows)
-    R = sps.csr_matrix((np.ones(n_rows), (users, movies)), shape=(n_users, n_movies))
-    R.data[:] = 1.0
-    Ru = sps.diags(1.0 / np.sqrt(np.maximum(1, np.asarray(R.sum(1)).ravel()))) @ R
-    Rm = sps.diags(1.0 / np.sqrt(np.maximum(1, np.asarray(R.sum(0)).ravel()))) @ R.T
-    user_block = sps.hstack([sps.eye(n_users), Ru]).tocsr()
-    movie_block = sps.hstack([sps.eye(n_movies), Rm]).tocsr()
-    main = sps.csr_matrix((np.ones(n_rows), (np.arange(n_rows), days)), shape=(n_rows, n_days))
-    y = 3.5 + rng.normal(0, 0.3, n_users)[users] + rng.normal(0, 0.3, n_movies)[movies] + rng.normal(0, 0.9, n_rows)
-    return main, (users, user_block), (movies, movie_block), y, [n_days, n_users, n_movies, n_movies, n_users]
-
-
 def test_c3_relation_blocks_rank16(engine, oracle):
-    main, ub, mb, y, gs = _ml1m_extended(30_000, 400, 250, 60, seed=1)
+    main, ub, mb, y, gs = ml1m_extended(30_000, 400, 250, 60, seed=1)
     trainer, chain = make_pair(engine, oracle, main, y, 16, "f64", X_rel=[ub, mb], group_shapes=gs)
     run_chain_parity(trainer, chain, "f64", 4)
+
+
+def test_c3_full_block_size_two_sweeps(engine, oracle):
+    """C3 at the size of BASELINE.json's configs[2] (bench.py --workload ml1m-ext): 900 188 rows, day one-hot
+    main table, user block 6 040 x 9 746 and movie block 3 706 x 9 746 with implicit-feedback columns
+    (one dependency level per implicit column), rank 16: two sweeps against the oracle, f64 at 1e-8."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    wl = bench.Workload("ml1m-ext")
+    assert wl.rel[0][1].shape == (6040, 9746) and wl.rel[1][1].shape == (3706, 9746) and wl.n_rows == 900_188
+    trainer, chain = make_pair(engine, oracle, wl.X, wl.y, wl.rank, "f64", X_rel=wl.rel, group_shapes=wl.group_shapes,
+                               n_iter=4)
+    run_chain_parity(trainer, chain, "f64", 2)
 
 
 def test_c4_full_size_two_sweeps_and_properties(engine, oracle):

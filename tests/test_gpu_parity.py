@@ -284,6 +284,42 @@ def test_device_mt19937_stream_matches_libstdcxx(engine, dtype, rank, monkeypatc
         np.testing.assert_allclose(a, b, rtol=tol, atol=0, err_msg=f"sweep {it}")
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_device_mt19937_farm_matches_libstdcxx(engine, dtype, monkeypatch):
+    """The parallel word generator (k_mt_farm: several lanes, each jumping over the words of the
+    others with the GF(2) jump polynomial of csrc/mt_jump.hpp) against libstdc++ draw for draw,
+    across several block boundaries: 4 lanes x 32768 words per block, ~85 k (f32) / ~170 k (f64)
+    words per sweep."""
+    from myfm_b200._myfm import ConfigBuilder, _TrainerHandle
+
+    X, y, group_shapes = movielens_like(4000, 700, 300, 3, seed=3)
+    cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat([0, 1], group_shapes))
+           .set_n_iter(8).set_n_kept_samples(8).build())
+
+    def variates(host: bool):
+        monkeypatch.delenv("MYFM_HOST_RNG", raising=False)
+        monkeypatch.delenv("MYFM_MT_FARM", raising=False)
+        if host:
+            monkeypatch.setenv("MYFM_HOST_RNG", "1")
+        else:
+            monkeypatch.setenv("MYFM_MT_FARM", "4,32768")
+        with engine.engine_options(dtype=dtype):
+            t = _TrainerHandle(X, [], y, 11, cfg)
+            t.init_fm(32, 0.1)
+        out = []
+        for _ in range(7):
+            t.step(1)
+            t.sync()
+            out.append(t.get_variates())
+        return out
+
+    dev, host = variates(False), variates(True)
+    tol = 1e-6 if dtype == "f32" else 1e-14
+    for it, (a, b) in enumerate(zip(dev, host)):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=tol, atol=0, err_msg=f"sweep {it}")
+
+
 def ordinal_1dim(n=1000):
     """The reference's ordered-probit fixture (tests/oprobit/test_oprobit_1dim.py:11-19)."""
     cps = np.asarray([0.0, 0.5, 1.5])
