@@ -268,15 +268,32 @@ def _as_csr(X) -> sps.csr_matrix:
     return X
 
 
+def _fingerprint(X: sps.csr_matrix) -> tuple:
+    """Cheap content check of a cached upload: strided samples of values / indices plus their ends.
+    In-place edits of a matrix between two predictions change it (a full checksum would cost as much
+    as the upload the cache saves)."""
+    n = X.nnz
+    if n == 0:
+        return (0,)
+    step = max(1, n // 1024)
+    return (float(X.data[::step].sum()), int(X.indices[::step].astype(np.int64).sum()), float(X.data[-1]),
+            int(X.indptr[-1]))
+
+
+def clear_dataset_cache() -> None:
+    """Drops the cached device copies of prediction matrices (and the host references pinning them)."""
+    _dataset_cache.clear()
+
+
 def _device_dataset(X, relations: Sequence[RelationBlock]) -> _DeviceDataset:
     """Per-iteration callbacks predict on the same test matrix every sweep
-    (reference src/myfm/utils/callbacks/libfm.py:82-113); keep the last few uploads alive,
-    keyed by the identity of the underlying buffers (mutating a matrix in place between two
-    predictions is not detected)."""
+    (reference src/myfm/utils/callbacks/libfm.py:82-113); keep the last few uploads alive, keyed by
+    the identity of the underlying buffers and a sampled fingerprint of their contents
+    (`clear_dataset_cache()` releases them)."""
     opts = get_options()
     X = _as_csr(X)
     key = (X.data.ctypes.data, X.indices.ctypes.data, X.indptr.ctypes.data, X.shape, X.nnz,
-           tuple(id(r) for r in relations), opts.dtype, opts.device)
+           tuple(id(r) for r in relations), opts.dtype, opts.device, _fingerprint(X))
     for k, _, ds in _dataset_cache:
         if k == key:
             return ds
@@ -813,6 +830,7 @@ def create_train_fm(
         history.hypers.append(hyper)
         if callback(it, live, hyper, history):
             break
+    trainer.sync()  # raises if the device flagged an error (every get_hyper() above checks as well)
     for g in range(trainer.n_cutpoint_groups):
         history.n_mh_accept.append(trainer.mh_accept(g))
     return predictor, history

@@ -7,6 +7,7 @@
 #include "host_data.hpp"
 #include "kernels.cuh"
 #include "field_sweep.cuh"
+#include "tile_sweep.cuh"
 #include "latent_device.cuh"
 #include "mt_device.cuh"
 #include "mt_jump.hpp"
@@ -21,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 namespace myfm {
 
@@ -511,6 +513,10 @@ template <typename Real> struct Trainer : TrainerBase {
       throw std::invalid_argument("unknown rng.");
     philox_latents = o.rng == MYFM_RNG_PHILOX;
     latent_seed = (static_cast<uint64_t>(static_cast<uint32_t>(seed)) << 32) ^ 0x9E3779B97F4A7C15ull;
+    {
+      std::seed_seq seq{static_cast<uint32_t>(seed), 0x6d79666du, 0x63757470u}; // "myfm", "cutp"
+      cut_gen.seed(seq);
+    }
     world = o.world_size > 1 ? o.world_size : 1;
     if (world > 1) {
       if (!o.nccl_unique_id)
@@ -600,6 +606,8 @@ template <typename Real> struct Trainer : TrainerBase {
       setup_field_path(Xh, Xth, level, n_levels, n_rel);
       MYFM_CUDA(cudaStreamSynchronize(stream));
       tick("CSC upload + field path");
+      setup_tile_path(Xh);
+      tick("tile path");
     }
     perm_dev.upload(perm, stream);
     items.upload(plan.items, stream);
@@ -667,7 +675,7 @@ template <typename Real> struct Trainer : TrainerBase {
       y.upload(y_dev, stream);
       MYFM_CUDA(cudaStreamSynchronize(stream));
     }
-    eq_buf.alloc(2 * static_cast<size_t>(N));
+    eq_buf.alloc(2 * static_cast<size_t>(N) + 2); // one spare pair: the tile path's bulk copies move 16 bytes at a time
     eq_buf.zero(stream);
     dense_tmp.alloc(N);
     if (cfg.task_type == MYFM_TASK_ORDERED) { // BaseFMTrainer.hpp:79-104
@@ -735,13 +743,8 @@ template <typename Real> struct Trainer : TrainerBase {
     reset_graphs();
     if (rng_stream)
       cudaStreamSynchronize(rng_stream);
-    if (peer_ok && comm) { // no rank unmaps its buffer while a peer's last kernel may still read it
-      NcclApi &nccl = NcclApi::get();
-      if (peer_error.p && nccl.AllReduce(peer_error.p, peer_error.p, 1, ncclInt, ncclMax, comm, stream) == ncclSuccess)
-        cudaStreamSynchronize(stream);
-    }
     if (!peer_base.empty() || peer_local)
-      close_peer_exchange();
+      close_peer_exchange(peer_ok);
     if (comm)
       NcclApi::get().CommDestroy(comm);
     for (auto *evs : {z_copied, z_ready, z_free})
@@ -997,22 +1000,34 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaEventRecord(z_ready[slot], rng_stream));
   }
 
-  void check_rng_error() {
-    if (peer_ok) {
-      int perr = 0;
-      MYFM_CUDA(cudaMemcpyAsync(&perr, peer_error.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      MYFM_CUDA(cudaStreamSynchronize(stream));
-      if (perr)
-        throw std::runtime_error("row-sharded training: a peer rank never published its column statistics.");
+  // Device-side error flags (the word ring of the mt19937 stream ran dry; a peer rank never published
+  // its column statistics) are copied into pinned memory together with whatever the caller fetches
+  // next and examined after that fetch's synchronisation: sync() and every get_hyper() — i.e. once
+  // per sweep of create_train_fm — see them at no extra synchronisation.
+  PinnedBuf<int> err_host;
+  void queue_error_flags() {
+    if (!err_host.p) {
+      err_host.alloc(2);
+      err_host.p[0] = err_host.p[1] = 0;
     }
-    if (!device_rng)
+    if (peer_ok)
+      MYFM_CUDA(cudaMemcpyAsync(err_host.p, peer_error.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (device_rng)
+      MYFM_CUDA(cudaMemcpyAsync(err_host.p + 1, &mt_ctl.p->error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  }
+  void throw_on_error_flags() { // the stream has been synchronised since queue_error_flags()
+    if (!err_host.p)
       return;
-    int err = 0;
-    MYFM_CUDA(cudaMemcpyAsync(&err, &mt_ctl.p->error, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    MYFM_CUDA(cudaStreamSynchronize(stream));
-    if (err)
+    if (err_host.p[0])
+      throw std::runtime_error("row-sharded training: a peer rank never published its column statistics.");
+    if (err_host.p[1])
       throw std::runtime_error("device mt19937 stream: the word ring ran dry or a bulk segment found too few accepted "
                                "attempts (set MYFM_HOST_RNG=1).");
+  }
+  void check_rng_error() {
+    queue_error_flags();
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    throw_on_error_flags();
   }
 
   // Standardised variates of one sweep, in the reference's consumption order.
@@ -1379,13 +1394,39 @@ template <typename Real> struct Trainer : TrainerBase {
     if (!peer_ok)
       close_peer_exchange();
   }
-  void close_peer_exchange() {
+  // No collective here (a destructor runs whenever the host language drops the trainer, in any
+  // order across ranks, possibly after a peer has died): a rank frees its buffer only after every
+  // peer has said, by a flag written INTO that buffer, that its kernels no longer read it.  A
+  // peer that does not say so within a few seconds costs a leaked buffer, never a hang or a fault.
+  static constexpr size_t PEER_CLOSING_OFFSET = 64; // int[PEER_MAX_RANKS] inside the 256-byte header
+  void close_peer_exchange(bool handshake = false) {
+    bool all_done = true;
+    if (handshake && peer_local) {
+      const int one = 1;
+      for (int r = 0; r < static_cast<int>(peer_base.size()); r++) // this rank's kernels are done (streams synced)
+        if (peer_base[r] && r != my_rank)
+          cudaMemcpy(peer_base[r] + PEER_CLOSING_OFFSET + sizeof(int) * my_rank, &one, sizeof(int),
+                     cudaMemcpyHostToDevice);
+      const auto t0 = std::chrono::steady_clock::now();
+      for (;;) {
+        int flags[PEER_MAX_RANKS] = {0};
+        if (cudaMemcpy(flags, peer_local + PEER_CLOSING_OFFSET, sizeof(flags), cudaMemcpyDeviceToHost) != cudaSuccess)
+          break;
+        all_done = true;
+        for (int r = 0; r < world; r++)
+          all_done = all_done && (r == my_rank || flags[r] != 0);
+        if (all_done || std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 5.0)
+          break;
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      }
+      cudaGetLastError();
+    }
     for (int r = 0; r < static_cast<int>(peer_base.size()); r++)
       if (peer_base[r] && r != my_rank)
         cudaIpcCloseMemHandle(peer_base[r]);
     peer_base.clear();
-    if (peer_local)
-      cudaFree(peer_local);
+    if (peer_local && all_done)
+      cudaFree(peer_local); // otherwise leaked on purpose: a peer may still be reading it
     peer_local = nullptr;
     peer_ok = false;
   }
@@ -1395,6 +1436,14 @@ template <typename Real> struct Trainer : TrainerBase {
   PeerView<Real> peer_view() const {
     PeerView<Real> pv;
     pv.world = world, pv.counter = peer_counter(), pv.elems = peer_stat_elems, pv.error = peer_error.p;
+    {
+      static const double seconds = [] {
+        const char *env = std::getenv("MYFM_PEER_TIMEOUT_S");
+        const double v = env ? std::atof(env) : 0.0;
+        return v > 0 ? v : 120.0;
+      }();
+      pv.timeout_ns = static_cast<unsigned long long>(seconds * 1e9);
+    }
     pv.my_posted = reinterpret_cast<unsigned long long *>(peer_local);
     pv.done = reinterpret_cast<unsigned int *>(peer_local + 16);
     for (int r = 0; r < world; r++) {
@@ -1404,6 +1453,206 @@ template <typename Real> struct Trainer : TrainerBase {
     return pv;
   }
   DevBuf<int> peer_error;
+
+  // ---- tile path (tile_sweep.cuh): two fields, row tiles staged in shared memory -----------------
+  bool tile_path = false;
+  int t_n_tiles = 0, t_n_colsL = 0;
+  uint32_t t_eq_bytes = 0;
+  size_t t_smem = 0;
+  DevBuf<int> t_tile_row, t_item_ptr, t_n_cta, t_colsL;
+  DevBuf<SweepItem> t_items;
+  DevBuf<unsigned> t_b_ent;
+  DevBuf<Real> t_b_val, t_part, t_pend;
+
+  // Cuts the rows into tiles of whole first-field columns and builds, per tile, the first-field work
+  // items and the sliced-ELL "B order" of the last field.  Xh: CSR in device row order.
+  void setup_tile_path(const HostCs<Real> &Xh) {
+    tile_path = false;
+    const char *off = std::getenv("MYFM_NO_TILE_PATH");
+    if ((off && off[0] == '1') || !field_path || f_tail != 1 || world > 1)
+      return;
+    const int64_t n = Xh.n_major;
+    int dev_smem = 0;
+    MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const size_t tab_bytes = (static_cast<size_t>(f_tab) * sizeof(Real) + 15) / 16 * 16;
+    const size_t reserve = 2048; // the kernel's static shared memory
+    if (static_cast<size_t>(dev_smem) < tab_bytes + reserve + 32 * 1024)
+      return;
+    int64_t cap = static_cast<int64_t>((dev_smem - reserve - tab_bytes) / (2 * sizeof(Real))) - 2;
+    {
+      const char *env = std::getenv("MYFM_TILE_ROWS"); // smaller tiles (tests: many tiles on small data)
+      if (env && std::atoll(env) >= 64)
+        cap = std::min<int64_t>(cap, std::atoll(env));
+    }
+    cap = std::min<int64_t>(cap, TILE_MAX_ROWS) & ~int64_t(1);
+    // first-field columns in row order; empty ones are dealt out afterwards
+    std::vector<SweepItem> cols, empty;
+    int longest = 0;
+    for (const SweepItem &it : f_items0_host) {
+      if (it.hi > it.lo)
+        cols.push_back(it), longest = std::max(longest, it.hi - it.lo);
+      else
+        empty.push_back(it);
+    }
+    if (longest > cap || cols.empty())
+      return;
+    std::sort(cols.begin(), cols.end(), [](const SweepItem &x, const SweepItem &y) { return x.lo < y.lo; });
+    // as many tiles as a whole number of waves over the SMs needs, each near `goal` rows
+    int64_t n_target = static_cast<int64_t>(f_sm_count) * ceil_div(n, static_cast<int64_t>(0.97 * cap) * f_sm_count);
+    if (n / n_target < 2048)
+      n_target = std::max<int64_t>(1, n / 2048);
+    std::vector<int> tile_row{0}, tile_first_col{0};
+    {
+      int64_t remaining_rows = n, remaining_tiles = n_target, rows = 0;
+      int64_t goal = std::min<int64_t>(cap, ceil_div(remaining_rows, remaining_tiles));
+      for (size_t c = 0; c < cols.size(); c++) {
+        const int len = cols[c].hi - cols[c].lo;
+        if (rows > 0 && (rows + len > cap || rows + len / 2 > goal)) {
+          tile_row.push_back(cols[c].lo), tile_first_col.push_back(static_cast<int>(c));
+          remaining_rows -= rows, remaining_tiles = std::max<int64_t>(1, remaining_tiles - 1), rows = 0;
+          goal = std::min<int64_t>(cap, ceil_div(remaining_rows, remaining_tiles));
+        }
+        rows += len;
+      }
+      tile_row.push_back(static_cast<int>(n)), tile_first_col.push_back(static_cast<int>(cols.size()));
+    }
+    const int n_tiles = static_cast<int>(tile_row.size()) - 1;
+    // first-field items per tile, longest first; empty columns round-robin
+    std::vector<std::vector<SweepItem>> per_tile(n_tiles);
+    for (int t = 0; t < n_tiles; t++)
+      per_tile[t].assign(cols.begin() + tile_first_col[t], cols.begin() + tile_first_col[t + 1]);
+    for (size_t k = 0; k < empty.size(); k++)
+      per_tile[k % n_tiles].push_back(empty[k]);
+    std::vector<int> item_ptr{0}, n_cta(n_tiles, 0);
+    std::vector<SweepItem> items;
+    for (int t = 0; t < n_tiles; t++) {
+      auto &v = per_tile[t];
+      std::stable_sort(v.begin(), v.end(),
+                       [](const SweepItem &x, const SweepItem &y) { return x.hi - x.lo > y.hi - y.lo; });
+      for (const SweepItem &it : v)
+        n_cta[t] += (it.hi - it.lo > TILE_CTA_MIN);
+      items.insert(items.end(), v.begin(), v.end());
+      item_ptr.push_back(static_cast<int>(items.size()));
+    }
+    // B order of every tile: its rows sorted by (last-field column, row), one word per row
+    if (f_tab > TILE_MAX_TAB)
+      return;
+    const int L = main_row_len;
+    std::vector<unsigned> b_ent(n);
+    std::vector<Real> b_val(main_unit ? 0 : n);
+    parallel_parts(std::min(parts_for(n * 4), n_tiles), [&](int part, int n_parts) {
+      std::vector<int> cnt(f_tab + 1, 0), touched;
+      for (int t = part; t < n_tiles; t += n_parts) { // counting sort by column, stable in the row
+        const int r0 = tile_row[t], r1 = tile_row[t + 1];
+        touched.clear();
+        for (int i = r0; i < r1; i++) {
+          const int c = Xh.idx[static_cast<size_t>(i) * L + (L - 1)] - f_last_base;
+          if (cnt[c]++ == 0)
+            touched.push_back(c);
+        }
+        std::sort(touched.begin(), touched.end());
+        int at = r0;
+        for (int c : touched) {
+          const int k = cnt[c];
+          cnt[c] = at, at += k;
+        }
+        for (int i = r0; i < r1; i++) {
+          const size_t p = static_cast<size_t>(i) * L + (L - 1);
+          const int c = Xh.idx[p] - f_last_base;
+          const int dst = cnt[c]++;
+          b_ent[dst] = (static_cast<unsigned>(i - r0) << 16) | static_cast<unsigned>(c);
+          if (!main_unit)
+            b_val[dst] = Xh.val[p];
+        }
+        for (int c : touched)
+          cnt[c] = 0;
+      }
+    });
+    std::vector<int> colsL;
+    for (size_t j = 0; j < f_level_host.size(); j++)
+      if (f_level_host[j] == L - 1)
+        colsL.push_back(static_cast<int>(j));
+    t_n_tiles = n_tiles, t_n_colsL = static_cast<int>(colsL.size());
+    t_eq_bytes = static_cast<uint32_t>((static_cast<size_t>(cap) + 2) * 2 * sizeof(Real) + 15) / 16 * 16;
+    t_smem = t_eq_bytes + tab_bytes;
+    t_tile_row.upload(tile_row, stream), t_item_ptr.upload(item_ptr, stream), t_n_cta.upload(n_cta, stream);
+    t_items.upload(items, stream);
+    t_b_ent.upload(b_ent, stream);
+    if (!main_unit)
+      t_b_val.upload(b_val, stream);
+    t_colsL.upload(colsL, stream);
+    t_part.alloc(2 * static_cast<size_t>(f_tab) * n_tiles); // [tile][column]; absent (tile, column) pairs stay zero
+    t_part.zero(stream);
+    t_pend.alloc(2 * static_cast<size_t>(f_tab));
+    t_pend.zero(stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream)); // host staging vectors die here
+    tile_path = true;
+  }
+
+  template <bool IS_V, bool UNIT, int PEND> void launch_tile_sweep(const TileArgs<Real> &a) {
+    auto kernel = k_tile_sweep<Real, IS_V, UNIT, PEND>;
+    static size_t configured = 0; // per instantiation
+    if (t_smem > configured) {
+      MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(t_smem)));
+      configured = t_smem;
+    }
+    kernel<<<t_n_tiles, TILE_THREADS, t_smem, stream>>>(a);
+    launched();
+  }
+
+  // One vector over a two-field table on the tile path: k_tile_sweep, then k_tile_fold.
+  template <bool IS_V>
+  void sweep_tile(Real *theta, Real *theta_t, int64_t t_stride, const Real *z, const Real *lambda, const Real *mu) {
+    TimedSpan span(timer, stream, 0);
+    const int pend = !f_pending_valid ? PEND_NONE : (IS_V && f_pending_is_v ? PEND_V : PEND_W);
+    {
+      TimedSpan span_stream(timer, stream, 3);
+      TileArgs<Real> a;
+      a.tile_row = t_tile_row.p, a.tile_item_ptr = t_item_ptr.p, a.tile_n_cta = t_n_cta.p;
+      a.item = reinterpret_cast<const int4 *>(t_items.p);
+      a.b_ent = t_b_ent.p, a.b_val = t_b_val.p;
+      a.n_tiles = t_n_tiles, a.eq_bytes = t_eq_bytes;
+      a.eq = eq();
+      a.own_val = f_own_val.p;
+      a.theta = theta, a.theta_t = theta_t, a.t_stride = t_stride;
+      a.z = z, a.group = group.p, a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
+      a.last_base = f_last_base, a.n_tab = f_tab;
+      a.pend = reinterpret_cast<const Pair<Real> *>(t_pend.p);
+      a.part = reinterpret_cast<Pair<Real> *>(t_part.p);
+#define MYFM_TS(V, P)                                                                              \
+  if (main_unit)                                                                                   \
+    launch_tile_sweep<V, true, P>(a);                                                              \
+  else                                                                                             \
+    launch_tile_sweep<V, false, P>(a);
+      if (!IS_V) {
+        if (pend != PEND_NONE)
+          throw std::logic_error("tile path: the w sweep must not find a pending update.");
+        MYFM_TS(false, PEND_NONE)
+      } else if (pend == PEND_NONE) {
+        MYFM_TS(true, PEND_NONE)
+      } else if (pend == PEND_W) {
+        MYFM_TS(true, PEND_W)
+      } else {
+        MYFM_TS(true, PEND_V)
+      }
+#undef MYFM_TS
+    }
+    {
+      TimedSpan span_fold(timer, stream, 4);
+      TileFoldArgs<Real> f;
+      f.cols = t_colsL.p, f.n_cols = t_n_colsL, f.n_tiles = t_n_tiles, f.last_base = f_last_base, f.n_tab = f_tab;
+      f.part = reinterpret_cast<const Pair<Real> *>(t_part.p);
+      f.theta = theta, f.theta_t = theta_t, f.t_stride = t_stride;
+      f.z = z, f.group = group.p, f.alpha = hv().alpha, f.lambda = lambda, f.mu = mu;
+      f.pend = reinterpret_cast<Pair<Real> *>(t_pend.p);
+      f.to_peer = 0, f.peer.world = 0, f.peer_local = nullptr, f.colstat = nullptr;
+      if (t_n_colsL) {
+        k_tile_fold<Real, IS_V><<<ceil_div(t_n_colsL, 32), 256, 0, stream>>>(f);
+        launched();
+      }
+    }
+    f_pending_valid = true, f_pending_is_v = IS_V;
+  }
 
   template <bool IS_V, bool UNIT, int PEND> void launch_field_stream(const FieldStreamArgs<Real> &a, int mode) {
     if (IS_V && f_tail > 1)
@@ -1601,7 +1850,9 @@ template <typename Real> struct Trainer : TrainerBase {
       w.zero(stream); // e keeps the stale contribution until update_e, as in the reference
       return;
     }
-    if (field_path)
+    if (tile_path)
+      sweep_tile<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
+    else if (field_path)
       sweep_field<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
     else
       sweep_main<false>(w.p, nullptr, 0, z, h.lambda_w, h.mu_w);
@@ -1632,6 +1883,10 @@ template <typename Real> struct Trainer : TrainerBase {
       Real *Vr = V.p + static_cast<size_t>(D_all) * r;
       const Real *z = z_all + static_cast<size_t>(D_all) * r;
       const Real *lam = h.lambda_V + static_cast<size_t>(G) * r, *mu = h.mu_V + static_cast<size_t>(G) * r;
+      if (tile_path) {
+        sweep_tile<true>(Vr, Vt.p + r, K, z, lam, mu);
+        continue;
+      }
       if (field_path) {
         sweep_field<true>(Vr, Vt.p + r, K, z, lam, mu);
         continue;
@@ -1774,7 +2029,7 @@ template <typename Real> struct Trainer : TrainerBase {
         if (start)
           cg.sampler->start();
         else
-          cg.sampler->step(rng.gen);
+          cg.sampler->step(cut_gen); // not rng.gen: the device stream took that state over in setup_rng
         cg.cutpoints = cg.sampler->gamma_now;
         const int n_group = static_cast<int>(cg.rows.size());
         if (!n_group)
@@ -1817,6 +2072,11 @@ template <typename Real> struct Trainer : TrainerBase {
     import_component(0, e_host.data());
   }
   DevBuf<Real> lat_gamma;
+  // PHILOX mode: the Metropolis-Hastings move of the cut-points (normals, chi-square, acceptance
+  // uniform) draws from its own generator.  The sweep's Gaussian / Gamma variates continue the
+  // mt19937(seed) stream on the device from the state the host generator had after create_FM, so
+  // stepping the host copy here would replay the words of the first sweeps.
+  std::mt19937 cut_gen;
 
   // eq component (0 = e, 1 = q) <-> a dense host vector in the caller's row order
   void export_component(int comp, Real *host) {
@@ -2050,7 +2310,9 @@ template <typename Real> struct Trainer : TrainerBase {
   }
   void get_hyper(double *alpha, double *mu_w, double *lambda_w, double *mu_V, double *lambda_V) override {
     require_fm();
+    queue_error_flags();
     auto hh = fetch(hyper.p, hyper_size());
+    throw_on_error_flags();
     *alpha = hh[0];
     for (int g = 0; g < G; g++)
       mu_w[g] = hh[2 + g], lambda_w[g] = hh[2 + G + g];
@@ -2130,7 +2392,11 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaStreamSynchronize(stream));
   }
   int64_t launch_count() const override { return launches; }
-  int sweep_path() const override { return field_path ? (peer_ok ? 2 : 1) + (f_exclusive ? 2 : 0) : 0; }
+  int sweep_path() const override {
+    if (tile_path)
+      return 5;
+    return field_path ? (peer_ok ? 2 : 1) + (f_exclusive ? 2 : 0) : 0;
+  }
   std::unique_ptr<SampleBase> snapshot() override { // device-to-device copy of the current sample
     require_fm();
     MYFM_CUDA(cudaSetDevice(device));

@@ -61,6 +61,7 @@ template <typename Real> struct PeerView {
   const Real *stat[PEER_MAX_RANKS];  // every rank's statistics buffers (buffer 0, then buffer 1)
   const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's published sequence number
   int *error;                    // set when a peer never shows up
+  unsigned long long timeout_ns; // how long peer_wait polls before it gives up (fatal)
   // producer: where this rank's partial statistics of the NEXT collective go
   __device__ __forceinline__ Real *produce(Real *local_stat) const {
     return local_stat + ((*counter + 1) & 1) * elems;
@@ -85,18 +86,33 @@ template <typename Real> __device__ __forceinline__ void peer_post_when_last(con
   }
 }
 
-// Block-wide: returns once every rank has published `seq` (bounded: a dead peer raises the error flag).
+// Block-wide: returns once every rank has published `seq`.  A peer that does not show up within
+// pv.timeout_ns (a rank that died, or one held up on the host for that long: MYFM_PEER_TIMEOUT_S,
+// default 120 s) is fatal: the flag is raised and the kernel traps, so the chain can never continue
+// on stale statistics — the next call on this trainer fails with a CUDA error.
+__device__ __forceinline__ unsigned long long peer_clock_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 template <typename Real> __device__ __forceinline__ void peer_wait(const PeerView<Real> &pv) {
   if (pv.world == 0)
     return;
   if (threadIdx.x < pv.world) {
     const unsigned long long seq = *pv.counter; // the collective this rank published last
     const volatile unsigned long long *flag = pv.posted[threadIdx.x];
-    long long spins = 0;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
     while (*flag < seq) {
-      if (++spins > (1ll << 23)) { // a few seconds of polling over NVLink
-        *pv.error = 3;
-        break;
+      if ((++spins & 0xfffu) == 0) { // look at the clock every 4096 polls
+        const unsigned long long now = peer_clock_ns();
+        if (t0 == 0)
+          t0 = now;
+        else if (now - t0 > pv.timeout_ns) {
+          *pv.error = 3;
+          __threadfence_system();
+          __trap();
+        }
       }
     }
     __threadfence_system();

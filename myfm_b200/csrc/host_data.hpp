@@ -78,7 +78,11 @@ template <typename Real> HostCs<Real> host_from_api(const myfm_csr_t &m, const c
   HostCs<Real> out;
   out.n_major = m.n_rows;
   out.n_minor = m.n_cols;
+  if (m.n_rows > 0 && m.indptr[0] != 0)
+    throw std::invalid_argument(std::string(what) + ": indptr[0] must be 0 (pass a canonical CSR, not a slice view).");
   const int64_t nnz = m.n_rows ? m.indptr[m.n_rows] : 0;
+  if (nnz > 0 && (m.indices == nullptr || m.data == nullptr))
+    throw std::invalid_argument(std::string(what) + ": indices / data must not be NULL.");
   if (nnz < 0 || nnz >= std::numeric_limits<int>::max() ||
       m.n_rows >= std::numeric_limits<int>::max() || m.n_cols >= std::numeric_limits<int>::max())
     throw std::invalid_argument(std::string(what) +

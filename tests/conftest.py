@@ -31,3 +31,19 @@ def engine():
     import myfm_b200
 
     return myfm_b200
+
+
+# myfm_trainer_sweep_path values (include/myfm_b200.h)
+PATH_GENERAL, PATH_FIELD, PATH_TILE = 0, 1, 5
+
+
+@pytest.fixture(params=["tile", "field"])
+def two_field_path(request, monkeypatch):
+    """Two-field tables take the tile path (csrc/tile_sweep.cuh) on one GPU; MYFM_NO_TILE_PATH=1 keeps
+    them on the field path (csrc/field_sweep.cuh), which tables with more fields and row shards use.
+    Yields the sweep path the trainer must report."""
+    if request.param == "field":
+        monkeypatch.setenv("MYFM_NO_TILE_PATH", "1")
+        return PATH_FIELD
+    monkeypatch.delenv("MYFM_NO_TILE_PATH", raising=False)
+    return PATH_TILE

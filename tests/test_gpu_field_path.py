@@ -12,10 +12,17 @@ from test_gpu_parity import assert_state_close, make_pair, run_chain_parity
 pytestmark = pytest.mark.gpu
 
 
-def test_path_selection(engine, oracle):
+def test_path_selection(engine, oracle, monkeypatch):
     X, y, gs = movielens_like(5000, 60, 20, 3, seed=1)
     t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
+    assert t.sweep_path() == 5  # two fields, one GPU: tile path
+    monkeypatch.setenv("MYFM_NO_TILE_PATH", "1")
+    t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
     assert t.sweep_path() == 1
+    monkeypatch.delenv("MYFM_NO_TILE_PATH")
+    X3, y3, gs3 = fields_like(3000, [20, 10, 5], 2, seed=2)
+    t, _ = make_pair(engine, oracle, X3, y3, 3, "f64", group_shapes=gs3)
+    assert t.sweep_path() == 1  # three fields: field path
     os.environ["MYFM_NO_FIELD_PATH"] = "1"
     try:
         t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
@@ -32,14 +39,15 @@ def test_path_selection(engine, oracle):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_long_columns(engine, oracle, dtype):
+def test_long_columns(engine, oracle, dtype, two_field_path):
     """Heavy-tailed fields: level-0 columns above 1024 rows (whole CTA), 256..1024 (warp, two
-    passes), below (registers); last-level columns above 8192 entries (chunked statistics)."""
+    passes), below (registers); last-level columns above 8192 entries (chunked statistics).  On the
+    tile path: a first-field column above 4096 rows (whole CTA), B-order segments of thousands of rows."""
     X, y, gs = movielens_like(60000, 200, 12, 4, seed=3, zipf=1.0)
     lens = np.diff(X.tocsc().indptr)
-    assert lens[:200].max() > 1024 and lens[200:].max() > 8192 and lens[:200].min() < 256
+    assert lens[:200].max() > 4096 and lens[200:].max() > 8192 and lens[:200].min() < 256
     t, chain = make_pair(engine, oracle, X, y, 4, dtype, group_shapes=gs)
-    assert t.sweep_path() == 1
+    assert t.sweep_path() == two_field_path
     run_chain_parity(t, chain, dtype, 6 if dtype == "f64" else 3)
 
 
@@ -61,15 +69,15 @@ def test_four_unit_fields(engine, oracle):
 
 
 @pytest.mark.parametrize("kw", [dict(fit_linear=False), dict(fit_w0=False), dict(fit_linear=False, fit_w0=False)])
-def test_without_linear_or_bias(engine, oracle, kw):
+def test_without_linear_or_bias(engine, oracle, kw, two_field_path):
     """fit_linear=False: the first factor's streaming pass finds nothing pending."""
     X, y, gs = movielens_like(8000, 80, 30, 3, seed=7)
     t, chain = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs, **kw)
-    assert t.sweep_path() == 1
+    assert t.sweep_path() == two_field_path
     run_chain_parity(t, chain, "f64", 5)
 
 
-def test_rank_zero_and_one(engine, oracle):
+def test_rank_zero_and_one(engine, oracle, two_field_path):
     X, y, gs = movielens_like(4000, 50, 20, 2, seed=8)
     for rank in (0, 1):
         t, chain = make_pair(engine, oracle, X, y, rank, "f64", group_shapes=gs)
@@ -77,18 +85,18 @@ def test_rank_zero_and_one(engine, oracle):
 
 
 @pytest.mark.parametrize("task", ["classification", "ordered"])
-def test_latent_tasks(engine, oracle, task):
+def test_latent_tasks(engine, oracle, task, two_field_path):
     X, y, gs = movielens_like(3000, 40, 15, 2, seed=9)
     if task == "classification":
         y = (y > np.median(y)).astype(np.float64) * 2 - 1
     else:
         y = np.digitize(y, np.quantile(y, [0.33, 0.66])).astype(np.float64)
     t, chain = make_pair(engine, oracle, X, y, 3, "f64", task=task, group_shapes=gs)
-    assert t.sweep_path() == 1
+    assert t.sweep_path() == two_field_path
     run_chain_parity(t, chain, "f64", 4)
 
 
-def test_field_path_equals_general_path(engine, oracle):
+def test_field_path_equals_general_path(engine, oracle, two_field_path):
     """Same chain through both schedules: they differ in summation order only."""
     X, y, gs = fields_like(20000, [300, 60], 4, seed=10, unit=False)
     a, _ = make_pair(engine, oracle, X, y, 6, "f64", group_shapes=gs)
@@ -97,7 +105,7 @@ def test_field_path_equals_general_path(engine, oracle):
         b, _ = make_pair(engine, oracle, X, y, 6, "f64", group_shapes=gs)
     finally:
         del os.environ["MYFM_NO_FIELD_PATH"]
-    assert (a.sweep_path(), b.sweep_path()) == (1, 0)
+    assert (a.sweep_path(), b.sweep_path()) == (two_field_path, 0)
     for it in range(5):
         a.step(1)
         b.step(1)
