@@ -1459,17 +1459,21 @@ template <typename Real> struct Trainer : TrainerBase {
   int t_n_tiles = 0, t_n_colsL = 0;
   uint32_t t_eq_bytes = 0;
   size_t t_smem = 0;
-  DevBuf<int> t_tile_row, t_item_ptr, t_n_cta, t_colsL;
+  DevBuf<int> t_tile_row, t_item_ptr, t_n_cta, t_n_warp, t_b_ptr, t_colsL;
   DevBuf<SweepItem> t_items;
-  DevBuf<unsigned> t_b_ent;
-  DevBuf<Real> t_b_val, t_part, t_pend;
+  DevBuf<unsigned> t_b_ent, t_c_ent;
+  DevBuf<int> t_cls_ptr, t_long_ptr;
+  DevBuf<int4> t_long_run;
+  DevBuf<Real> t_b_val, t_c_val, t_part, t_pend;
 
   // Cuts the rows into tiles of whole first-field columns and builds, per tile, the first-field work
   // items and the sliced-ELL "B order" of the last field.  Xh: CSR in device row order.
   void setup_tile_path(const HostCs<Real> &Xh) {
     tile_path = false;
-    const char *off = std::getenv("MYFM_NO_TILE_PATH");
-    if ((off && off[0] == '1') || !field_path || f_tail != 1 || world > 1)
+    // Opt-in (MYFM_TILE_PATH=1): parity-green, but measured at 112 us per vector against the field
+    // path's 107 us on the ml10m workload (DESIGN.md section 3c has the profile), so not the default.
+    const char *on = std::getenv("MYFM_TILE_PATH");
+    if (!(on && on[0] == '1') || !field_path || f_tail != 1 || world > 1)
       return;
     const int64_t n = Xh.n_major;
     int dev_smem = 0;
@@ -1523,25 +1527,40 @@ template <typename Real> struct Trainer : TrainerBase {
       per_tile[t].assign(cols.begin() + tile_first_col[t], cols.begin() + tile_first_col[t + 1]);
     for (size_t k = 0; k < empty.size(); k++)
       per_tile[k % n_tiles].push_back(empty[k]);
-    std::vector<int> item_ptr{0}, n_cta(n_tiles, 0);
+    std::vector<int> item_ptr{0}, n_cta(n_tiles, 0), n_warp(n_tiles, 0);
     std::vector<SweepItem> items;
     for (int t = 0; t < n_tiles; t++) {
       auto &v = per_tile[t];
       std::stable_sort(v.begin(), v.end(),
                        [](const SweepItem &x, const SweepItem &y) { return x.hi - x.lo > y.hi - y.lo; });
-      for (const SweepItem &it : v)
+      for (const SweepItem &it : v) {
         n_cta[t] += (it.hi - it.lo > TILE_CTA_MIN);
-      items.insert(items.end(), v.begin(), v.end());
+        n_warp[t] += (it.hi - it.lo > TILE_TEAM_MAX && it.hi - it.lo <= TILE_CTA_MIN);
+      }
+      for (SweepItem it : v) {
+        it.first = static_cast<int>(cfg.group_index[it.col]); // the 4th word carries the column's group
+        items.push_back(it);
+      }
       item_ptr.push_back(static_cast<int>(items.size()));
     }
     // B order of every tile: its rows sorted by (last-field column, row), one word per row
     if (f_tab > TILE_MAX_TAB)
       return;
     const int L = main_row_len;
-    std::vector<unsigned> b_ent(n);
-    std::vector<Real> b_val(main_unit ? 0 : n);
+    std::vector<int> b_ptr(n_tiles + 1, 0); // every tile's B range starts at a multiple of TILE_VEC words
+    for (int t = 0; t < n_tiles; t++)
+      b_ptr[t + 1] = b_ptr[t] + (tile_row[t + 1] - tile_row[t] + TILE_VEC - 1) / TILE_VEC * TILE_VEC;
+    std::vector<unsigned> b_ent(b_ptr[n_tiles], TILE_NO_KEY);
+    std::vector<Real> b_val(main_unit ? 0 : b_ptr[n_tiles], Real(0));
+    struct TileRuns { // the statistics layout of one tile (tile_sweep.cuh: TileArgs::c_ent)
+      std::vector<unsigned> ent;
+      std::vector<Real> val;
+      int cls[7] = {0, 0, 0, 0, 0, 0, 0}; // slot offsets of the classes inside ent, [5] .. [6]: long runs
+      std::vector<int4> longs;          // first slot relative to ent
+    };
+    std::vector<TileRuns> tr(n_tiles);
     parallel_parts(std::min(parts_for(n * 4), n_tiles), [&](int part, int n_parts) {
-      std::vector<int> cnt(f_tab + 1, 0), touched;
+      std::vector<int> cnt(f_tab + 1, 0), touched, run_start, run_len;
       for (int t = part; t < n_tiles; t += n_parts) { // counting sort by column, stable in the row
         const int r0 = tile_row[t], r1 = tile_row[t + 1];
         touched.clear();
@@ -1551,7 +1570,8 @@ template <typename Real> struct Trainer : TrainerBase {
             touched.push_back(c);
         }
         std::sort(touched.begin(), touched.end());
-        int at = r0;
+        const int e0 = b_ptr[t]; // the tile's first B word
+        int at = e0;
         for (int c : touched) {
           const int k = cnt[c];
           cnt[c] = at, at += k;
@@ -1564,10 +1584,93 @@ template <typename Real> struct Trainer : TrainerBase {
           if (!main_unit)
             b_val[dst] = Xh.val[p];
         }
+        // runs in column order: run k = rows b_ent[run_start[k] .. + run_len[k])
+        run_start.clear(), run_len.clear();
+        {
+          int at2 = e0;
+          for (int c : touched) {
+            const int len = cnt[c] - at2; // cnt[c] now points behind the run
+            run_start.push_back(at2), run_len.push_back(len);
+            at2 += len;
+          }
+        }
+        TileRuns &o = tr[t];
+        size_t slots = 0;
+        for (int k = 0; k < 5; k++) {
+          const int c = 1 << k;
+          size_t in_class = 0;
+          for (int len : run_len)
+            if (len <= c && (k == 0 || len > c / 2))
+              in_class += c;
+          o.cls[k] = static_cast<int>(slots);
+          slots += (in_class + TILE_VEC - 1) / TILE_VEC * TILE_VEC;
+        }
+        o.cls[5] = static_cast<int>(slots);
+        size_t long_rows = 0;
+        for (int len : run_len)
+          if (len > 16)
+            long_rows += (len + 3) / 4 * 4;
+        o.cls[6] = static_cast<int>(slots + long_rows);
+        o.ent.assign(slots + long_rows, TILE_NO_KEY);
+        if (!main_unit)
+          o.val.assign(slots + long_rows, Real(0));
+        int fill_at[5];
+        for (int k = 0; k < 5; k++)
+          fill_at[k] = o.cls[k];
+        size_t long_at = slots;
+        for (size_t k = 0; k < run_len.size(); k++) {
+          const int len = run_len[k];
+          size_t dst;
+          if (len > 16) {
+            dst = long_at;
+            o.longs.push_back(make_int4(touched[k], static_cast<int>(long_at), (len + 3) / 4 * 4, 0));
+            long_at += (len + 3) / 4 * 4;
+          } else {
+            int cls = 0;
+            while ((1 << cls) < len)
+              cls++;
+            dst = fill_at[cls], fill_at[cls] += 1 << cls;
+          }
+          for (int i = 0; i < len; i++) {
+            o.ent[dst + i] = b_ent[run_start[k] + i];
+            if (!main_unit)
+              o.val[dst + i] = b_val[run_start[k] + i];
+          }
+        }
+        std::stable_sort(o.longs.begin(), o.longs.end(), [](const int4 &x, const int4 &y) { return x.z > y.z; });
         for (int c : touched)
           cnt[c] = 0;
       }
     });
+    size_t n_slots = 0, n_long = 0;
+    for (const TileRuns &o : tr)
+      n_slots += (o.ent.size() + TILE_VEC - 1) / TILE_VEC * TILE_VEC, n_long += o.longs.size();
+    if (n_slots >= static_cast<size_t>(std::numeric_limits<int>::max()))
+      return;
+    std::vector<unsigned> c_ent(n_slots, TILE_NO_KEY);
+    std::vector<Real> c_val(main_unit ? 0 : n_slots);
+    std::vector<int> cls_ptr(static_cast<size_t>(n_tiles) * 8, 0), long_ptr{0};
+    std::vector<int4> long_run;
+    long_run.reserve(n_long);
+    {
+      size_t at = 0;
+      for (int t = 0; t < n_tiles; t++) {
+        const TileRuns &o = tr[t];
+        std::copy(o.ent.begin(), o.ent.end(), c_ent.begin() + at);
+        if (!main_unit)
+          std::copy(o.val.begin(), o.val.end(), c_val.begin() + at);
+        for (int k = 0; k < 7; k++)
+          cls_ptr[static_cast<size_t>(t) * 8 + k] = static_cast<int>(at) + o.cls[k];
+        for (int4 r : o.longs) {
+          r.y += static_cast<int>(at);
+          long_run.push_back(r);
+        }
+        long_ptr.push_back(static_cast<int>(long_run.size()));
+        at += (o.ent.size() + TILE_VEC - 1) / TILE_VEC * TILE_VEC;
+      }
+    }
+    if (long_run.empty())
+      long_run.push_back(make_int4(0, 0, 0, 0)); // never read
     std::vector<int> colsL;
     for (size_t j = 0; j < f_level_host.size(); j++)
       if (f_level_host[j] == L - 1)
@@ -1576,10 +1679,13 @@ template <typename Real> struct Trainer : TrainerBase {
     t_eq_bytes = static_cast<uint32_t>((static_cast<size_t>(cap) + 2) * 2 * sizeof(Real) + 15) / 16 * 16;
     t_smem = t_eq_bytes + tab_bytes;
     t_tile_row.upload(tile_row, stream), t_item_ptr.upload(item_ptr, stream), t_n_cta.upload(n_cta, stream);
+    t_n_warp.upload(n_warp, stream), t_b_ptr.upload(b_ptr, stream);
     t_items.upload(items, stream);
     t_b_ent.upload(b_ent, stream);
+    t_c_ent.upload(c_ent, stream);
+    t_cls_ptr.upload(cls_ptr, stream), t_long_ptr.upload(long_ptr, stream), t_long_run.upload(long_run, stream);
     if (!main_unit)
-      t_b_val.upload(b_val, stream);
+      t_b_val.upload(b_val, stream), t_c_val.upload(c_val, stream);
     t_colsL.upload(colsL, stream);
     t_part.alloc(2 * static_cast<size_t>(f_tab) * n_tiles); // [tile][column]; absent (tile, column) pairs stay zero
     t_part.zero(stream);
@@ -1609,8 +1715,11 @@ template <typename Real> struct Trainer : TrainerBase {
       TimedSpan span_stream(timer, stream, 3);
       TileArgs<Real> a;
       a.tile_row = t_tile_row.p, a.tile_item_ptr = t_item_ptr.p, a.tile_n_cta = t_n_cta.p;
+      a.tile_n_warp = t_n_warp.p, a.tile_b_ptr = t_b_ptr.p;
       a.item = reinterpret_cast<const int4 *>(t_items.p);
       a.b_ent = t_b_ent.p, a.b_val = t_b_val.p;
+      a.c_ent = t_c_ent.p, a.c_val = t_c_val.p;
+      a.tile_cls_ptr = t_cls_ptr.p, a.tile_long_ptr = t_long_ptr.p, a.long_run = t_long_run.p;
       a.n_tiles = t_n_tiles, a.eq_bytes = t_eq_bytes;
       a.eq = eq();
       a.own_val = f_own_val.p;
@@ -1647,7 +1756,7 @@ template <typename Real> struct Trainer : TrainerBase {
       f.pend = reinterpret_cast<Pair<Real> *>(t_pend.p);
       f.to_peer = 0, f.peer.world = 0, f.peer_local = nullptr, f.colstat = nullptr;
       if (t_n_colsL) {
-        k_tile_fold<Real, IS_V><<<ceil_div(t_n_colsL, 32), 256, 0, stream>>>(f);
+        k_tile_fold<Real, IS_V><<<ceil_div(t_n_colsL, 32), 32 * FOLD_GROUPS, 0, stream>>>(f);
         launched();
       }
     }

@@ -18,11 +18,12 @@
 //      share x . theta of q_init (FMTrainer.hpp:320) in the tile;
 //   2. the first-field sweep (FMTrainer.hpp:237-254, :343-376): a warp per column, statistics ->
 //      draw -> update, on shared memory only (no global access per row when all values are 1);
-//   3. the tile's pairs go back with one bulk store (shared -> global) WHILE a second B pass forms
-//      the last field's statistics: one thread per row, a segmented warp scan over equal columns,
-//      runs that continue across iterations carried in registers, runs that continue across warps
-//      joined in warp order — every (column, tile) sum has a fixed order.  k_tile_fold adds a
-//      column's tile sums in tile order, draws, and leaves {theta_old, theta_new} pending.
+//   3. the tile's pairs go back with one bulk store (shared -> global) WHILE the last field's
+//      statistics are formed: the rows once more, grouped by run (= the rows of one last-field
+//      column inside the tile) and laid out by padded run length, so that a warp iteration reduces
+//      32 / c aligned runs of c slots with log2(c) butterfly steps (no keys, no carries; long runs
+//      take a warp each) — every (column, tile) sum has a fixed order.  k_tile_fold adds a column's
+//      tile sums in a fixed order, draws, and leaves {theta_old, theta_new} pending.
 //
 // Every random access of the sweep is a shared-memory access; global memory sees only streams:
 // per row and vector 16 B of {e, q} (one read, one write) and 2 x 4 B of B order.  Element-wise
@@ -83,15 +84,35 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // writes made through the generic proxy (ordinary st.shared) become visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+constexpr int TILE_VEC = 128;      // slots per warp iteration of the B passes: one 16-byte load per lane
+constexpr int TILE_TEAM = 8;       // lanes per first-field column of up to TILE_TEAM_MAX rows (4 columns per warp)
+constexpr int TILE_TEAM_MAX = 256;
+
 template <typename Real> struct TileArgs {
   // tiles (static, built once per fit: engine.cu setup_tile_path)
   const int *tile_row;        // [n_tiles + 1] first row of every tile
   const int *tile_item_ptr;   // [n_tiles + 1] into item
-  const int *tile_n_cta;      // [n_tiles] leading items of the tile handled by the whole CTA
-  const int4 *item;           // first-field columns {column, first row, end row, -}, longest first per tile
-  const unsigned *b_ent;      // [n_rows] B order: entries [tile_row[t], tile_row[t+1]) are tile t's rows sorted by
-                              // (last-field column, row) as (row - tile_row[t]) << 16 | (column - last_base)
-  const Real *b_val;          // [n_rows] last-field value of every B entry (unused when UNIT)
+  const int *tile_n_cta;      // [n_tiles] leading items of the tile handled by the whole CTA (> TILE_CTA_MIN rows)
+  const int *tile_n_warp;     // [n_tiles] following items handled by a warp each (> TILE_TEAM_MAX rows)
+  const int4 *item;           // first-field columns {column, first row, end row, group}, longest first per tile
+  // B order: the tile's rows sorted by (last-field column, row), one word per row:
+  // (row - tile_row[t]) << 16 | (column - last_base); every tile's range starts at a multiple of
+  // TILE_VEC words and is padded to one with TILE_NO_KEY.
+  const unsigned *b_ent;
+  const Real *b_val;          // last-field value of every B entry (unused when UNIT)
+  const int *tile_b_ptr;      // [n_tiles + 1] word offsets of the tiles in b_ent
+  // The same rows once more for the statistics of the last field, grouped by RUN (the rows of one
+  // last-field column inside the tile, ascending): runs of up to 16 rows are padded to 1, 2, 4, 8 or
+  // 16 slots (TILE_NO_KEY) and stored class by class, every class a multiple of TILE_VEC slots.  A
+  // lane loads 4 consecutive slots, so runs of up to 4 rows are summed inside a lane and longer ones
+  // with one or two butterfly steps; runs above 16 rows are stored behind the classes (each padded
+  // to a multiple of 4 slots) and take a warp each.
+  const unsigned *c_ent;
+  const Real *c_val;          // last-field value per slot (unused when UNIT)
+  const int *tile_cls_ptr;    // [n_tiles][8]: slot offsets of the classes 1, 2, 4, 8, 16 ([k] .. [k+1]), k = 0 .. 4;
+                              // [5] .. [6]: the long runs' slots
+  const int *tile_long_ptr;   // [n_tiles + 1] into long_run
+  const int4 *long_run;       // {column - last_base, first slot, slots (multiple of 4), -}, longest first per tile
   int n_tiles;
   uint32_t eq_bytes;          // shared-memory bytes reserved for the pairs (the table follows)
   // rows
@@ -107,6 +128,11 @@ template <typename Real> struct TileArgs {
   const Pair<Real> *pend; // [n_tab] {theta_old, theta_new} left pending by the previous vector
   Pair<Real> *part;       // [n_tiles][n_tab] last-field statistics of every tile
 };
+
+// L2 prefetch of a whole range with one TMA instruction (16-byte granularity).
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
 // Sum of two values over the CTA, broadcast (one barrier pair for both).
 template <typename Real> __device__ __forceinline__ void tile_block_sum2(Real &a, Real &b, Real *scratch) {
@@ -150,34 +176,104 @@ __device__ __forceinline__ void tile_column_update(const TileArgs<Real> &a, Pair
   }
 }
 
-// Inclusive sums over runs of equal keys (sorted: a run is contiguous) inside a warp.
-template <typename Real>
-__device__ __forceinline__ void tile_run_scan(unsigned key, Real &sa, Real &sb, int lane) {
+template <typename Real> __device__ __forceinline__ void tile_store_run(Pair<Real> *part, unsigned ent, Real sa, Real sb) {
+  Pair<Real> out;
+  out.x = sa, out.y = sb;
+  __stcg(part + (ent & 0xffffu), out);
+}
+
+// Statistics of the runs of class C (slots per run) in the warp iterations [it_lo, it_hi) of TILE_VEC
+// slots: lane l owns the slots 4 l .. 4 l + 3 of an iteration.
+template <typename Real, bool IS_V, bool UNIT, int C>
+__device__ __forceinline__ void tile_class_pass(const TileArgs<Real> &a, const Pair<Real> *s_eq_tile, const Real *s_tab,
+                                                Pair<Real> *part, int it_lo, int it_hi, int lane, Real alpha) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(a.c_ent) + lane;
+  uint4 nxt = __ldcs(src + static_cast<size_t>(it_lo) * (TILE_VEC / 4));
+  for (int it = it_lo; it < it_hi; it++) {
+    const uint4 e4 = nxt;
+    if (it + 1 < it_hi) // the next iteration's slots are on their way while this one is reduced
+      nxt = __ldcs(src + static_cast<size_t>(it + 1) * (TILE_VEC / 4));
+    const size_t at = static_cast<size_t>(it) * TILE_VEC + 4 * lane;
+    const unsigned ent[4] = {e4.x, e4.y, e4.z, e4.w};
+    Real sa[4], sb[4];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const Real ua = __shfl_up_sync(FULL_MASK, sa, d), ub = __shfl_up_sync(FULL_MASK, sb, d);
-    const unsigned uk = __shfl_up_sync(FULL_MASK, key, d);
-    if (lane >= d && uk == key)
-      sa += ua, sb += ub;
+    for (int k = 0; k < 4; k++) {
+      sa[k] = 0, sb[k] = 0;
+      if (ent[k] != TILE_NO_KEY) {
+        const Real x = UNIT ? Real(1) : __ldcs(a.c_val + at + k);
+        const Pair<Real> v = s_eq_tile[ent[k] >> 16];
+        field_stats<Real, IS_V>(v.x, v.y, x, s_tab[ent[k] & 0xffffu], alpha, sa[k], sb[k]);
+      }
+    }
+    if (C == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (ent[k] != TILE_NO_KEY)
+          tile_store_run(part, ent[k], sa[k], sb[k]);
+    } else if (C == 2) {
+      if (ent[0] != TILE_NO_KEY)
+        tile_store_run(part, ent[0], sa[0] + sa[1], sb[0] + sb[1]);
+      if (ent[2] != TILE_NO_KEY)
+        tile_store_run(part, ent[2], sa[2] + sa[3], sb[2] + sb[3]);
+    } else {
+      Real ta = (sa[0] + sa[1]) + (sa[2] + sa[3]), tb = (sb[0] + sb[1]) + (sb[2] + sb[3]);
+#pragma unroll
+      for (int o = 1; o < C / 4; o <<= 1) {
+        ta += __shfl_xor_sync(FULL_MASK, ta, o);
+        tb += __shfl_xor_sync(FULL_MASK, tb, o);
+      }
+      if ((lane & (C / 4 - 1)) == 0 && ent[0] != TILE_NO_KEY)
+        tile_store_run(part, ent[0], ta, tb);
+    }
   }
 }
 
-// What a warp leaves for the join of runs across warps: its first and its last run.
-template <typename Real> struct TileRunRecord {
-  unsigned first_col, last_col; // TILE_NO_KEY: none
-  Real first_a, first_b, last_a, last_b;
-};
+// One warp iteration of the first B pass: pending update of the last field and its share of q_init
+// for the four rows of this lane.
+template <typename Real, bool IS_V, bool UNIT, int PEND>
+__device__ __forceinline__ void tile_pending_pass(const TileArgs<Real> &a, Pair<Real> *s_eq_tile, const Real *s_tab,
+                                                  uint4 e4, size_t at) {
+  const unsigned ent[4] = {e4.x, e4.y, e4.z, e4.w};
+  Pair<Real> tt[4];
+  Real xv[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    xv[k] = Real(1);
+    tt[k].x = 0, tt[k].y = 0;
+    if (ent[k] != TILE_NO_KEY) {
+      if (PEND != PEND_NONE)
+        tt[k] = __ldg(a.pend + (ent[k] & 0xffffu));
+      if (!UNIT)
+        xv[k] = __ldcs(a.b_val + at + k);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (ent[k] != TILE_NO_KEY) {
+      const Real x = xv[k];
+      Pair<Real> v = s_eq_tile[ent[k] >> 16];
+      if (PEND == PEND_V) { // FMTrainer.hpp:366-374 of the previous factor's last-field column
+        const Real h = x * (v.y - x * tt[k].x);
+        v.x = v.x + h * (tt[k].y - tt[k].x);
+      } else if (PEND == PEND_W) { // FMTrainer.hpp:240,251
+        v.x = (v.x - x * tt[k].x) + x * tt[k].y;
+      }
+      if (IS_V)
+        v.y = x * s_tab[ent[k] & 0xffffu];
+      s_eq_tile[ent[k] >> 16] = v;
+    }
+}
 
-constexpr int TILE_BU = 4; // B entries per thread in flight
+constexpr int TILE_P1_PRE = 8; // warp iterations of the first B pass loaded before the tile has arrived
 
 template <typename Real, bool IS_V, bool UNIT, int PEND>
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_sweep(const __grid_constant__ TileArgs<Real> a) {
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_counter;
+  __shared__ int s_counter[2];
   __shared__ Real s_scratch[2 * TILE_WARPS];
-  __shared__ TileRunRecord<Real> s_rec[TILE_WARPS];
   constexpr int AR = 16 / static_cast<int>(sizeof(Pair<Real>)); // rows per 16 bytes (bulk copy granularity)
+  constexpr bool HAS_P1 = IS_V || PEND != PEND_NONE;
   const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row0 = a.tile_row[tile], row1 = a.tile_row[tile + 1];
@@ -185,71 +281,80 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_sweep(const __grid_con
   Pair<Real> *s_eq = reinterpret_cast<Pair<Real> *>(tile_smem) - first;  // s_eq[i]: global row i
   Real *s_tab = reinterpret_cast<Real *>(tile_smem + a.eq_bytes);
   const uint32_t bytes = static_cast<uint32_t>(last - first) * sizeof(Pair<Real>);
+  const int b0 = a.tile_b_ptr[tile], b1 = a.tile_b_ptr[tile + 1];
+  const int *cp = a.tile_cls_ptr + tile * 8;
 
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    s_counter = 0;
+    s_counter[0] = s_counter[1] = 0;
   }
   __syncthreads();
-  if (threadIdx.x == 0 && bytes) {
-    mbar_expect_tx(&s_bar, bytes);
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(a.eq + first);
-    for (uint32_t off = 0; off < bytes; off += TILE_BULK_CHUNK)
-      bulk_load(tile_smem + off, src + off, min(TILE_BULK_CHUNK, bytes - off), &s_bar);
+  if (threadIdx.x == 0) {
+    if (bytes) {
+      mbar_expect_tx(&s_bar, bytes);
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(a.eq + first);
+      for (uint32_t off = 0; off < bytes; off += TILE_BULK_CHUNK)
+        bulk_load(tile_smem + off, src + off, min(TILE_BULK_CHUNK, bytes - off), &s_bar);
+    }
+    // the index streams of the B passes on their way into L2 meanwhile
+    if (HAS_P1 && b1 > b0) {
+      bulk_prefetch_l2(a.b_ent + b0, static_cast<uint32_t>(b1 - b0) * 4u);
+      if (!UNIT)
+        bulk_prefetch_l2(a.b_val + b0, static_cast<uint32_t>(b1 - b0) * static_cast<uint32_t>(sizeof(Real)));
+    }
+    if (cp[6] > cp[0]) {
+      bulk_prefetch_l2(a.c_ent + cp[0], static_cast<uint32_t>(cp[6] - cp[0]) * 4u);
+      if (!UNIT)
+        bulk_prefetch_l2(a.c_val + cp[0], static_cast<uint32_t>(cp[6] - cp[0]) * static_cast<uint32_t>(sizeof(Real)));
+    }
   }
-  // the last field's values of this vector while the rows are in flight
-  for (int t = threadIdx.x; t < a.n_tab; t += TILE_THREADS)
-    s_tab[t] = a.theta[a.last_base + t];
+  // While the rows are in flight: this warp's share of the first B pass (a contiguous range of warp
+  // iterations) goes into registers, and the last field's values of this vector into the table.
+  const int p1_n = (b1 - b0) / TILE_VEC, p1_per = (p1_n + TILE_WARPS - 1) / TILE_WARPS;
+  const int p1_lo = min(p1_n, warp * p1_per), p1_hi = min(p1_n, p1_lo + p1_per);
+  const uint4 *p1_src = reinterpret_cast<const uint4 *>(a.b_ent + b0) + lane;
+  uint4 p1_pre[TILE_P1_PRE];
+  if (HAS_P1) {
+#pragma unroll
+    for (int k = 0; k < TILE_P1_PRE; k++)
+      if (p1_lo + k < p1_hi)
+        p1_pre[k] = __ldcs(p1_src + static_cast<size_t>(p1_lo + k) * (TILE_VEC / 4));
+  }
+  for (int t0 = threadIdx.x; t0 < a.n_tab; t0 += 4 * TILE_THREADS) {
+    Real tv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      tv[u] = t0 + u * TILE_THREADS < a.n_tab ? a.theta[a.last_base + t0 + u * TILE_THREADS] : Real(0);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (t0 + u * TILE_THREADS < a.n_tab)
+        s_tab[t0 + u * TILE_THREADS] = tv[u];
+  }
   const Real alpha = *a.alpha;
-  // this warp's share of the B order: a contiguous range, a multiple of 32 entries
-  const int per_warp = ((row1 - row0 + TILE_THREADS - 1) / TILE_THREADS) * 32;
-  const int b_lo = min(row1, row0 + warp * per_warp), b_hi = min(row1, b_lo + per_warp);
   if (bytes)
     mbar_wait(&s_bar, 0);
   __syncthreads();
 
   // ---- 1. B pass: pending update of the last field; its share of q_init -------------------------
-  if (IS_V || PEND != PEND_NONE) {
-    for (int base = b_lo + lane; base < b_hi; base += 32 * TILE_BU) {
-      unsigned ent[TILE_BU];
-      Real xv[TILE_BU];
-      Pair<Real> tt[TILE_BU];
+  if (HAS_P1) {
+    Pair<Real> *s_eq_tile = s_eq + row0;
 #pragma unroll
-      for (int u = 0; u < TILE_BU; u++) {
-        const int p = base + 32 * u;
-        ent[u] = p < b_hi ? __ldcs(a.b_ent + p) : TILE_NO_KEY;
-        xv[u] = (UNIT || p >= b_hi) ? Real(1) : __ldcs(a.b_val + p);
-      }
-      if (PEND != PEND_NONE) {
-#pragma unroll
-        for (int u = 0; u < TILE_BU; u++)
-          if (ent[u] != TILE_NO_KEY)
-            tt[u] = __ldg(a.pend + (ent[u] & 0xffffu));
-      }
-#pragma unroll
-      for (int u = 0; u < TILE_BU; u++)
-        if (ent[u] != TILE_NO_KEY) {
-          const int i = row0 + static_cast<int>(ent[u] >> 16);
-          const Real x = xv[u];
-          Pair<Real> v = s_eq[i];
-          if (PEND == PEND_V) { // FMTrainer.hpp:366-374 of the previous factor's last-field column
-            const Real h = x * (v.y - x * tt[u].x);
-            v.x = v.x + h * (tt[u].y - tt[u].x);
-          } else if (PEND == PEND_W) { // FMTrainer.hpp:240,251
-            v.x = (v.x - x * tt[u].x) + x * tt[u].y;
-          }
-          if (IS_V)
-            v.y = x * s_tab[ent[u] & 0xffffu];
-          s_eq[i] = v;
-        }
-    }
+    for (int k = 0; k < TILE_P1_PRE; k++)
+      if (p1_lo + k < p1_hi)
+        tile_pending_pass<Real, IS_V, UNIT, PEND>(a, s_eq_tile, s_tab, p1_pre[k],
+                                                  static_cast<size_t>(b0) + static_cast<size_t>(p1_lo + k) * TILE_VEC +
+                                                      4 * lane);
+    for (int it = p1_lo + TILE_P1_PRE; it < p1_hi; it++) // tiles beyond TILE_P1_PRE * 4096 rows
+      tile_pending_pass<Real, IS_V, UNIT, PEND>(a, s_eq_tile, s_tab,
+                                                __ldcs(p1_src + static_cast<size_t>(it) * (TILE_VEC / 4)),
+                                                static_cast<size_t>(b0) + static_cast<size_t>(it) * TILE_VEC + 4 * lane);
     __syncthreads();
   }
 
   // ---- 2. first field: statistics, draw, update on shared memory --------------------------------
   {
     const int it0 = a.tile_item_ptr[tile], it1 = a.tile_item_ptr[tile + 1];
-    const int n_cta = a.tile_n_cta[tile];
+    const int n_cta = a.tile_n_cta[tile], n_warp = a.tile_n_warp[tile];
     for (int c = it0; c < it0 + n_cta; c++) { // very long columns: the whole CTA
       const int4 it = __ldg(a.item + c);
       const int j = it.x, g = a.group[j];
@@ -266,45 +371,72 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_sweep(const __grid_con
           a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
       }
     }
-    // One warp per column, longest first, handed out in batches; lane b of the warp owns the
-    // scalars of the batch's b-th column (one chain of dependent loads per batch, not per column).
-    const int n_warp_items = it1 - it0 - n_cta;
-    const int batch = max(1, min(32, n_warp_items / (2 * TILE_WARPS)));
+    // long columns: a warp each, handed out one at a time (longest first)
     for (;;) {
-      int c0 = 0;
+      int c = 0;
       if (lane == 0)
-        c0 = atomicAdd(&s_counter, batch);
-      c0 = __shfl_sync(FULL_MASK, c0, 0);
-      if (c0 >= n_warp_items)
+        c = atomicAdd(&s_counter[0], 1);
+      c = __shfl_sync(FULL_MASK, c, 0);
+      if (c >= n_warp)
         break;
-      const int n_b = min(batch, n_warp_items - c0);
-      int4 my_it = make_int4(0, 0, 0, 0);
-      Real my_theta = 0, my_lam = 0, my_mu = 0, my_z = 0;
-      if (lane < n_b) {
-        my_it = __ldg(a.item + it0 + n_cta + c0 + lane);
-        my_theta = a.theta[my_it.x];
-        my_z = a.z[my_it.x];
-        const int g = a.group[my_it.x];
-        my_lam = a.lambda[g], my_mu = a.mu[g];
-      }
-      Real my_new = 0;
-      for (int bi = 0; bi < n_b; bi++) {
-        const int lo = __shfl_sync(FULL_MASK, my_it.y, bi), hi = __shfl_sync(FULL_MASK, my_it.z, bi);
-        const Real theta_old = __shfl_sync(FULL_MASK, my_theta, bi), lam = __shfl_sync(FULL_MASK, my_lam, bi);
-        const Real mu = __shfl_sync(FULL_MASK, my_mu, bi), z = __shfl_sync(FULL_MASK, my_z, bi);
-        Real sq = 0, lin = 0;
-        tile_column_stats<Real, IS_V, UNIT>(a, s_eq, lo, hi, lane, 32, theta_old, alpha, sq, lin);
-        sq = warp_sum(sq), lin = warp_sum(lin);
-        const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
-        tile_column_update<Real, IS_V, UNIT>(a, s_eq, lo, hi, lane, 32, theta_old, theta_new);
-        if (lane == bi)
-          my_new = theta_new;
-      }
-      if (lane < n_b) {
-        a.theta[my_it.x] = my_new;
+      const int4 it = __ldg(a.item + it0 + n_cta + c);
+      const int j = it.x, g = a.group[j];
+      const Real theta_old = a.theta[j];
+      const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
+      Real sq = 0, lin = 0;
+      tile_column_stats<Real, IS_V, UNIT>(a, s_eq, it.y, it.z, lane, 32, theta_old, alpha, sq, lin);
+      sq = warp_sum(sq), lin = warp_sum(lin);
+      const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+      tile_column_update<Real, IS_V, UNIT>(a, s_eq, it.y, it.z, lane, 32, theta_old, theta_new);
+      if (lane == 0) {
+        a.theta[j] = theta_new;
         if (a.theta_t)
-          a.theta_t[static_cast<int64_t>(my_it.x) * a.t_stride] = my_new;
+          a.theta_t[static_cast<int64_t>(j) * a.t_stride] = theta_new;
       }
+    }
+    // the other columns (up to TILE_TEAM_MAX rows): TILE_TEAM lanes each, four columns per warp at a time,
+    // so four chains of statistics -> draw -> update are in flight per warp
+    const int team0 = it0 + n_cta + n_warp, n_team = it1 - team0;
+    const int team = lane / TILE_TEAM, tl = lane % TILE_TEAM;
+    constexpr int TEAMS = 32 / TILE_TEAM;
+    // (the item of the next round is fetched while this round's columns are swept)
+    int c0 = 0;
+    if (lane == 0)
+      c0 = atomicAdd(&s_counter[1], TEAMS);
+    c0 = __shfl_sync(FULL_MASK, c0, 0);
+    int4 it = make_int4(0, 0, 0, 0);
+    if (c0 + team < n_team)
+      it = __ldg(a.item + team0 + c0 + team);
+    while (c0 < n_team) {
+      const bool live = c0 + team < n_team;
+      Real theta_old = 0, lam = 0, mu = 0, z = 0;
+      if (live) { // the lanes of a team read the same words; it.w = the column's group
+        theta_old = a.theta[it.x];
+        z = a.z[it.x];
+        lam = a.lambda[it.w], mu = a.mu[it.w];
+      }
+      int c_next = 0;
+      if (lane == 0)
+        c_next = atomicAdd(&s_counter[1], TEAMS);
+      c_next = __shfl_sync(FULL_MASK, c_next, 0);
+      int4 it_next = make_int4(0, 0, 0, 0);
+      if (c_next + team < n_team)
+        it_next = __ldg(a.item + team0 + c_next + team);
+      Real sq = 0, lin = 0;
+      tile_column_stats<Real, IS_V, UNIT>(a, s_eq, it.y, it.z, tl, TILE_TEAM, theta_old, alpha, sq, lin);
+#pragma unroll
+      for (int o = TILE_TEAM / 2; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(FULL_MASK, sq, o);
+        lin += __shfl_xor_sync(FULL_MASK, lin, o);
+      }
+      const Real theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+      tile_column_update<Real, IS_V, UNIT>(a, s_eq, it.y, it.z, tl, TILE_TEAM, theta_old, theta_new);
+      if (live && tl == 0) {
+        a.theta[it.x] = theta_new;
+        if (a.theta_t)
+          a.theta_t[static_cast<int64_t>(it.x) * a.t_stride] = theta_new;
+      }
+      c0 = c_next, it = it_next;
     }
   }
   fence_async_smem();
@@ -331,110 +463,46 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_sweep(const __grid_con
   }
   {
     Pair<Real> *part = a.part + static_cast<size_t>(tile) * a.n_tab;
-    // the run that reaches the end of the entries seen so far (all lanes hold the same copy)
-    unsigned carry_col = TILE_NO_KEY;
-    Real carry_a = 0, carry_b = 0;
-    bool first_done = false;
-    TileRunRecord<Real> rec;
-    rec.first_col = rec.last_col = TILE_NO_KEY;
-    rec.first_a = rec.first_b = rec.last_a = rec.last_b = 0;
-    auto store_run = [&](unsigned col, Real sa, Real sb) {
-      Pair<Real> out;
-      out.x = sa, out.y = sb;
-      __stcg(part + col, out);
-    };
-    for (int base = b_lo; base < b_hi; base += 32 * TILE_BU) {
-      unsigned ent[TILE_BU];
-      Real xv[TILE_BU];
-#pragma unroll
-      for (int u = 0; u < TILE_BU; u++) {
-        const int p = base + 32 * u + lane;
-        ent[u] = p < b_hi ? __ldcs(a.b_ent + p) : TILE_NO_KEY;
-        xv[u] = (UNIT || p >= b_hi) ? Real(1) : __ldcs(a.b_val + p);
-      }
-#pragma unroll
-      for (int u = 0; u < TILE_BU; u++) {
-        if (base + 32 * u >= b_hi) // warp-uniform
-          break;
-        const unsigned key = ent[u] == TILE_NO_KEY ? TILE_NO_KEY : (ent[u] & 0xffffu);
-        Real sa = 0, sb = 0;
-        if (key != TILE_NO_KEY) {
-          const Pair<Real> v = s_eq[row0 + static_cast<int>(ent[u] >> 16)];
-          field_stats<Real, IS_V>(v.x, v.y, xv[u], s_tab[key], alpha, sa, sb);
-        }
-        tile_run_scan(key, sa, sb, lane);
-        const unsigned next_key = __shfl_down_sync(FULL_MASK, key, 1);
-        const unsigned head_key = __shfl_sync(FULL_MASK, key, 0);
-        const int n_valid = __popc(__ballot_sync(FULL_MASK, key != TILE_NO_KEY)); // valid lanes: 0 .. n_valid - 1
-        // Every branch below is warp-uniform (carry_*, first_done and `tails` are the same in all lanes).
-        // The carried run either continues into this iteration's head run or is finished; a finished
-        // run is final unless it is the warp's first one, which waits for the join across warps.
-        if (carry_col != TILE_NO_KEY) {
-          if (carry_col == head_key) {
-            if (key == head_key)
-              sa = carry_a + sa, sb = carry_b + sb;
-          } else {
-            if (!first_done)
-              rec.first_col = carry_col, rec.first_a = carry_a, rec.first_b = carry_b;
-            else if (lane == 0)
-              store_run(carry_col, carry_a, carry_b);
-            first_done = true;
-          }
-        }
-        const bool is_tail = key != TILE_NO_KEY && (lane == n_valid - 1 || next_key != key);
-        const bool finished = is_tail && lane != n_valid - 1; // the run of the last valid lane is carried on
-        const unsigned tails = __ballot_sync(FULL_MASK, finished);
-        if (tails) {
-          int src = -1;
-          if (!first_done) {
-            src = __ffs(tails) - 1;
-            rec.first_col = __shfl_sync(FULL_MASK, key, src);
-            rec.first_a = __shfl_sync(FULL_MASK, sa, src), rec.first_b = __shfl_sync(FULL_MASK, sb, src);
-            first_done = true;
-          }
-          if (finished && lane != src)
-            store_run(key, sa, sb);
-        }
-        carry_col = __shfl_sync(FULL_MASK, key, n_valid - 1);
-        carry_a = __shfl_sync(FULL_MASK, sa, n_valid - 1);
-        carry_b = __shfl_sync(FULL_MASK, sb, n_valid - 1);
-      }
-    }
-    if (carry_col != TILE_NO_KEY) {
-      if (!first_done)
-        rec.first_col = carry_col, rec.first_a = carry_a, rec.first_b = carry_b; // one run in the whole range
-      else
-        rec.last_col = carry_col, rec.last_a = carry_a, rec.last_b = carry_b;
-    }
-    if (lane == 0)
-      s_rec[warp] = rec;
-    __syncthreads();
-    if (threadIdx.x == 0) { // runs that continue across warps: joined in warp order
-      unsigned col = TILE_NO_KEY;
+    const Pair<Real> *s_eq_tile = s_eq + row0;
+    // short runs: every warp takes a contiguous range of the warp iterations of all five classes
+    const int i_begin = cp[0] / TILE_VEC, i_end = cp[5] / TILE_VEC;
+    const int per = (i_end - i_begin + TILE_WARPS - 1) / TILE_WARPS;
+    const int my_lo = min(i_end, i_begin + warp * per), my_hi = min(i_end, my_lo + per);
+#define MYFM_CLASS(K, C)                                                                           \
+  {                                                                                                \
+    const int lo = max(my_lo, cp[K] / TILE_VEC), hi = min(my_hi, cp[K + 1] / TILE_VEC);             \
+    if (lo < hi)                                                                                   \
+      tile_class_pass<Real, IS_V, UNIT, C>(a, s_eq_tile, s_tab, part, lo, hi, lane, alpha);        \
+  }
+    MYFM_CLASS(0, 1)
+    MYFM_CLASS(1, 2)
+    MYFM_CLASS(2, 4)
+    MYFM_CLASS(3, 8)
+    MYFM_CLASS(4, 16)
+#undef MYFM_CLASS
+    // long runs: a warp each
+    for (int r = a.tile_long_ptr[tile] + warp; r < a.tile_long_ptr[tile + 1]; r += TILE_WARPS) {
+      const int4 run = __ldg(a.long_run + r);
+      const Real theta_col = s_tab[run.x];
       Real sa = 0, sb = 0;
-      auto flush = [&]() {
-        if (col != TILE_NO_KEY) {
-          Pair<Real> out;
-          out.x = sa, out.y = sb;
-          __stcg(part + col, out);
-        }
-      };
-      for (int w = 0; w < TILE_WARPS; w++) {
-        const TileRunRecord<Real> r = s_rec[w];
-        if (r.first_col != TILE_NO_KEY) {
-          if (r.first_col == col) {
-            sa += r.first_a, sb += r.first_b;
-          } else {
-            flush();
-            col = r.first_col, sa = r.first_a, sb = r.first_b;
+#pragma unroll 2
+      for (int p = run.y + 4 * lane; p < run.y + run.z; p += TILE_VEC) {
+        const uint4 e4 = __ldcs(reinterpret_cast<const uint4 *>(a.c_ent + p));
+        const unsigned ent[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (ent[k] != TILE_NO_KEY) {
+            const Real x = UNIT ? Real(1) : __ldcs(a.c_val + p + k);
+            const Pair<Real> v = s_eq_tile[ent[k] >> 16];
+            field_stats<Real, IS_V>(v.x, v.y, x, theta_col, alpha, sa, sb);
           }
-        }
-        if (r.last_col != TILE_NO_KEY) {
-          flush();
-          col = r.last_col, sa = r.last_a, sb = r.last_b;
-        }
       }
-      flush();
+      sa = warp_sum(sa), sb = warp_sum(sb);
+      if (lane == 0) {
+        Pair<Real> out;
+        out.x = sa, out.y = sb;
+        __stcg(part + run.x, out);
+      }
     }
   }
   if (threadIdx.x == 0)
@@ -459,10 +527,11 @@ template <typename Real> struct TileFoldArgs {
   Real *peer_local, *colstat;
 };
 
-// 256 threads = 32 columns x 8 tile groups: warp g adds the tiles g, g + 8, ... of 32 neighbouring
-// columns (coalesced rows of `part`), warp 0 joins the 8 groups in group order and draws.
-constexpr int FOLD_GROUPS = 8;
-template <typename Real, bool IS_V> __global__ void __launch_bounds__(256) k_tile_fold(TileFoldArgs<Real> a) {
+// 512 threads = 32 columns x 16 tile groups: warp g adds the tiles g, g + 16, ... of 32 neighbouring
+// columns (coalesced rows of `part`), warp 0 joins the groups in group order and draws.
+constexpr int FOLD_GROUPS = 16;
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(32 * FOLD_GROUPS) k_tile_fold(TileFoldArgs<Real> a) {
   __shared__ Real s_sum[FOLD_GROUPS][2][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int w = blockIdx.x * 32 + lane;
@@ -470,7 +539,7 @@ template <typename Real, bool IS_V> __global__ void __launch_bounds__(256) k_til
   const int j = live ? a.cols[w] : 0, c = j - a.last_base;
   Real sq = 0, lin = 0;
   if (live) {
-#pragma unroll 4
+#pragma unroll 8
     for (int t = grp; t < a.n_tiles; t += FOLD_GROUPS) {
       const Pair<Real> v = __ldcg(a.part + static_cast<size_t>(t) * a.n_tab + c);
       sq += v.x, lin += v.y;

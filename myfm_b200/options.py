@@ -2,7 +2,8 @@
 
 The estimator signatures stay exactly the reference's, so the knobs of the CUDA engine live
 here: ``myfm_b200.engine_options(dtype="f32")`` as a context manager or a plain setter, with
-``MYFM_B200_DTYPE`` / ``MYFM_B200_RNG`` / ``MYFM_B200_DEVICE`` as environment defaults.
+``MYFM_B200_DTYPE`` / ``MYFM_B200_RNG`` / ``MYFM_B200_DEVICE`` (or ``MYFM_DTYPE`` / ``MYFM_RNG`` /
+``MYFM_DEVICE``) as environment defaults.
 
 dtype  "f64" (default; what the reference ships, cpp_source/bind.cpp) or "f32" (the reference's
        bind_float.cpp instantiation; the fast path the benchmarks use).
@@ -17,11 +18,16 @@ from dataclasses import dataclass, replace
 from typing import Iterator, Optional
 
 
+def _env(name: str, default: str) -> str:
+    """MYFM_B200_<name>, or the shorter MYFM_<name>."""
+    return os.environ.get("MYFM_B200_" + name, os.environ.get("MYFM_" + name, default))
+
+
 @dataclass(frozen=True)
 class EngineOptions:
-    dtype: str = os.environ.get("MYFM_B200_DTYPE", "f64")
-    rng: str = os.environ.get("MYFM_B200_RNG", "mt19937")
-    device: int = int(os.environ.get("MYFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    dtype: str = _env("DTYPE", "f64")
+    rng: str = _env("RNG", "mt19937")
+    device: int = int(_env("DEVICE", os.environ.get("LOCAL_RANK", "0")))
     # row-sharded data parallelism (set by myfm_b200.distributed)
     world_size: int = 1
     rank: int = 0

@@ -39,11 +39,11 @@ PATH_GENERAL, PATH_FIELD, PATH_TILE = 0, 1, 5
 
 @pytest.fixture(params=["tile", "field"])
 def two_field_path(request, monkeypatch):
-    """Two-field tables take the tile path (csrc/tile_sweep.cuh) on one GPU; MYFM_NO_TILE_PATH=1 keeps
-    them on the field path (csrc/field_sweep.cuh), which tables with more fields and row shards use.
+    """Two-field tables take the field path (csrc/field_sweep.cuh) by default; MYFM_TILE_PATH=1 selects the
+    tile path (csrc/tile_sweep.cuh: row tiles staged in shared memory by TMA bulk copies) on one GPU.
     Yields the sweep path the trainer must report."""
-    if request.param == "field":
-        monkeypatch.setenv("MYFM_NO_TILE_PATH", "1")
-        return PATH_FIELD
-    monkeypatch.delenv("MYFM_NO_TILE_PATH", raising=False)
-    return PATH_TILE
+    if request.param == "tile":
+        monkeypatch.setenv("MYFM_TILE_PATH", "1")
+        return PATH_TILE
+    monkeypatch.delenv("MYFM_TILE_PATH", raising=False)
+    return PATH_FIELD

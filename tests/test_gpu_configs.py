@@ -70,7 +70,7 @@ def test_c4_full_size_two_sweeps_and_properties(engine, oracle):
 
     X, y, gs, rank = bench.make_workload("ml10m")
     trainer, chain = make_pair(engine, oracle, X, y, rank, "f32", group_shapes=gs, n_iter=4)
-    assert trainer.sweep_path() == 5  # the tile path (csrc/tile_sweep.cuh)
+    assert trainer.sweep_path() == 1  # the field path (csrc/field_sweep.cuh)
     twin, _unused = None, None
     for it in range(2):
         trainer.step(1)

@@ -15,14 +15,14 @@ pytestmark = pytest.mark.gpu
 def test_path_selection(engine, oracle, monkeypatch):
     X, y, gs = movielens_like(5000, 60, 20, 3, seed=1)
     t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
-    assert t.sweep_path() == 5  # two fields, one GPU: tile path
-    monkeypatch.setenv("MYFM_NO_TILE_PATH", "1")
+    assert t.sweep_path() == 1  # field path
+    monkeypatch.setenv("MYFM_TILE_PATH", "1")
     t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)
-    assert t.sweep_path() == 1
-    monkeypatch.delenv("MYFM_NO_TILE_PATH")
+    assert t.sweep_path() == 5  # two fields, one GPU, opted in: tile path
     X3, y3, gs3 = fields_like(3000, [20, 10, 5], 2, seed=2)
     t, _ = make_pair(engine, oracle, X3, y3, 3, "f64", group_shapes=gs3)
-    assert t.sweep_path() == 1  # three fields: field path
+    assert t.sweep_path() == 1  # three fields: field path even when opted in
+    monkeypatch.delenv("MYFM_TILE_PATH")
     os.environ["MYFM_NO_FIELD_PATH"] = "1"
     try:
         t, _ = make_pair(engine, oracle, X, y, 3, "f64", group_shapes=gs)

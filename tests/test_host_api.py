@@ -157,3 +157,17 @@ def test_engine_options():
     assert myfm_b200.get_options() == before
     with pytest.raises(ValueError):
         myfm_b200.set_options(dtype="f16")
+
+
+def test_import_myfm_drop_in():
+    """The reference's package name resolves to the engine's modules of the same names."""
+    import myfm
+    import myfm_b200
+    from myfm import MyFMClassifier, MyFMOrderedProbit, MyFMRegressor, RelationBlock  # noqa: F401
+    from myfm._myfm import ConfigBuilder, create_train_fm  # noqa: F401
+    from myfm.utils.callbacks import ClassificationCallback, OrderedProbitCallback, RegressionCallback  # noqa: F401
+    import myfm.gibbs
+
+    assert MyFMRegressor is myfm_b200.MyFMRegressor and myfm.gibbs is myfm_b200.gibbs
+    assert set(myfm.__all__) >= {"RelationBlock", "MyFMOrderedProbit", "MyFMRegressor", "MyFMClassifier",
+                                 "MyFMGibbsRegressor", "MyFMGibbsClassifier"}
