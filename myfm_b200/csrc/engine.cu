@@ -401,6 +401,8 @@ template <typename Real> struct DevRelationTrain {
   DevBuf<Real> card, q, q_S, c, c_S, e, e_q;
   int n_levels = 0;
   DevBuf<int> level_ptr, level_cols;
+  DevBuf<int> run_end; // [n_levels] end of the run of single-column levels a level belongs to (k_rel_sweep_smem)
+  DevBuf<int4> level_rec;
   RelCache<Real> cache() { return RelCache<Real>{card.p, q.p, q_S.p, c.p, c_S.p, e.p, e_q.p}; }
 };
 
@@ -662,6 +664,23 @@ template <typename Real> struct Trainer : TrainerBase {
       t.n_levels = bp.n_levels;
       t.level_ptr.upload(bp.level_ptr, stream);
       t.level_cols.upload(bp.cols, stream);
+      {
+        std::vector<int> run_end(std::max(1, bp.n_levels), 0);
+        for (int lv = bp.n_levels - 1; lv >= 0; lv--) {
+          const bool single = bp.level_ptr[lv + 1] - bp.level_ptr[lv] == 1;
+          const bool next_single = lv + 1 < bp.n_levels && bp.level_ptr[lv + 2] - bp.level_ptr[lv + 1] == 1;
+          run_end[lv] = (single && next_single) ? run_end[lv + 1] : lv + 1;
+        }
+        t.run_end.upload(run_end, stream);
+        // {column, first entry, end entry, group} of the first column of every level
+        std::vector<int4> rec(std::max(1, bp.n_levels), make_int4(0, 0, 0, 0));
+        const int64_t off = data.rels[b].offset;
+        for (int lv = 0; lv < bp.n_levels; lv++) {
+          const int l = bp.cols[bp.level_ptr[lv]];
+          rec[lv] = make_int4(l, Bth.ptr[l], Bth.ptr[l + 1], static_cast<int>(cfg.group_index[off + l]));
+        }
+        t.level_rec.upload(rec, stream);
+      }
       MYFM_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -1948,7 +1967,22 @@ template <typename Real> struct Trainer : TrainerBase {
     a.t_stride = t_stride;
     a.z = z + d.offset, a.group = group.p + d.offset;
     a.alpha = hv().alpha, a.lambda = lambda, a.mu = mu;
-    k_rel_sweep<Real, IS_V><<<1, 1024, 0, stream>>>(a);
+    // block caches in shared memory when they fit (7 arrays of S reals), else in global memory
+    int dev_smem = 0;
+    MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const size_t smem = 7 * static_cast<size_t>(d.S) * sizeof(Real);
+    const char *no_smem = std::getenv("MYFM_REL_GLOBAL");
+    if (smem + 1024 <= static_cast<size_t>(dev_smem) && !(no_smem && no_smem[0] == '1')) {
+      auto kernel = k_rel_sweep_smem<Real, IS_V>;
+      static size_t configured = 0; // per instantiation
+      if (smem > configured) {
+        MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+      }
+      kernel<<<1, 512, smem, stream>>>(a, static_cast<int>(d.S), t.run_end.p, t.level_rec.p);
+    } else {
+      k_rel_sweep<Real, IS_V><<<1, 1024, 0, stream>>>(a);
+    }
     launched();
   }
 

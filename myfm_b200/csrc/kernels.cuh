@@ -960,6 +960,217 @@ __global__ void __launch_bounds__(1024) k_rel_sweep(RelSweepArgs<Real> a) {
   }
 }
 
+// The same sweep with the block caches in SHARED memory (f32: up to ~8 000 block rows).  Blocks with
+// SVD++-style implicit columns (examples/ml-1m-extended.ipynb: every column of the rated movies
+// touches ~150-250 block rows and consecutive columns share rows) degenerate to one column per
+// level: ~10^4 dependent steps per vector.  A level with one column is walked by ONE warp — no
+// block barrier per column, shared-memory latency instead of L2 latency in every dependent
+// step, the next column's entries fetched while the current one is reduced — and the other
+// warps sleep at the barrier that ends the run of single-column levels (run_end, host-built).
+// Arithmetic and order inside a column are those of rel_pass1 / rel_pass2 above.
+template <typename Real> struct RelSmem {
+  Real *card, *q, *q_S, *c, *c_S, *e, *e_q;
+};
+
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void rel_s_pass1(const RelSmem<Real> &m, int s, Real x, Real theta_old, Real &sq, Real &lin) {
+  if (IS_V) {
+    Real h_B = (m.q[s] - x * theta_old);
+    Real h2 = h_B * h_B * m.card[s] + 2 * m.c[s] * h_B + m.c_S[s];
+    h2 = x * x * h2;
+    sq += h2;
+    lin += (-m.e[s] * h_B - m.e_q[s]) * x;
+  } else {
+    sq += (x * x) * m.card[s];
+    lin += (-x) * m.e[s];
+  }
+}
+template <typename Real, bool IS_V>
+__device__ __forceinline__ void rel_s_pass2(const RelSmem<Real> &m, int s, Real x, Real theta_old, Real theta_new) {
+  const Real delta = theta_new - theta_old;
+  if (IS_V) {
+    Real h_B = m.q[s] - x * theta_old;
+    m.q[s] += delta * x;
+    m.q_S[s] += delta * (theta_new + theta_old) * x * x;
+    m.e[s] += x * delta * (h_B * m.card[s] + m.c[s]);
+    m.e_q[s] += x * delta * (h_B * m.c[s] + m.c_S[s]);
+  } else {
+    m.e[s] += (x * m.card[s]) * delta;
+  }
+}
+
+constexpr int REL_TEAM = 4; // warps walking a run of single-column levels
+constexpr int REL_REG = 3;  // entries per thread kept in registers (columns up to 32 * REL_TEAM * REL_REG entries)
+
+template <typename Real, bool IS_V>
+__global__ void __launch_bounds__(512)
+    k_rel_sweep_smem(RelSweepArgs<Real> a, int S, const int *__restrict__ run_end, const int4 *__restrict__ level_rec) {
+  extern __shared__ __align__(16) unsigned char rel_raw[];
+  __shared__ Real s_red[2 * REL_TEAM];
+  RelSmem<Real> m;
+  {
+    Real *base = reinterpret_cast<Real *>(rel_raw);
+    m.card = base, m.q = base + S, m.q_S = base + 2 * S, m.c = base + 3 * S, m.c_S = base + 4 * S;
+    m.e = base + 5 * S, m.e_q = base + 6 * S;
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    m.card[s] = a.cache.card[s];
+    m.e[s] = a.cache.e[s];
+    if (IS_V)
+      m.q[s] = a.cache.q[s], m.q_S[s] = a.cache.q_S[s], m.c[s] = a.cache.c[s], m.c_S[s] = a.cache.c_S[s],
+      m.e_q[s] = a.cache.e_q[s];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const Real alpha = *a.alpha;
+  for (int lv = 0; lv < a.n_levels;) {
+    const int cb = a.level_ptr[lv], ce = a.level_ptr[lv + 1];
+    if (ce - cb != 1) { // several columns, pairwise disjoint in their block rows: a warp each
+      for (int ci = cb + wid; ci < ce; ci += nwarps) {
+        const int l = a.level_cols[ci];
+        const int b = a.Bt.ptr[l], en = a.Bt.ptr[l + 1];
+        const Real theta_old = a.theta[l];
+        Real sq = 0, lin = 0;
+        for (int p = b + lane; p < en; p += 32)
+          rel_s_pass1<Real, IS_V>(m, a.Bt.idx[p], a.Bt.val[p], theta_old, sq, lin);
+        sq = warp_sum(sq);
+        lin = warp_sum(lin);
+        const int g = a.group[l];
+        const Real theta_new = rel_draw<Real, IS_V>(sq, lin, theta_old, alpha, a.lambda[g], a.mu[g], a.z[l]);
+        if (lane == 0) {
+          a.theta[l] = theta_new;
+          if (a.theta_t)
+            a.theta_t[static_cast<int64_t>(l) * a.t_stride] = theta_new;
+        }
+        for (int p = b + lane; p < en; p += 32)
+          rel_s_pass2<Real, IS_V>(m, a.Bt.idx[p], a.Bt.val[p], theta_old, theta_new);
+      }
+      __syncthreads();
+      lv++;
+      continue;
+    }
+    // A run of single-column levels [lv, lv_end): REL_TEAM warps (one per SM sub-partition, so the
+    // column's few hundred instructions issue four wide) walk it with two named barriers per column;
+    // the other warps sleep at the block barrier below.  Three columns are in flight: the record
+    // {column, first entry, end entry, group} of column k + 2 is being loaded, the scalars and entries
+    // of column k + 1 (addressed by its record) are being loaded, column k is being swept.
+    const int lv_end = run_end[lv];
+    if (wid < REL_TEAM) {
+      constexpr int NT = 32 * REL_TEAM;
+      const int tt = threadIdx.x; // 0 .. NT - 1
+      // column k + 1 (set 1) and column k + 2 (set 2) in flight
+      int idx_1[REL_REG], idx_2[REL_REG];
+      Real val_1[REL_REG], val_2[REL_REG];
+      Real theta_1 = 0, lam_1 = 0, mu_1 = 0, z_1 = 0, theta_2 = 0, lam_2 = 0, mu_2 = 0, z_2 = 0;
+      int4 rec_1 = level_rec[lv];
+      int4 rec_2 = lv + 1 < lv_end ? level_rec[lv + 1] : make_int4(0, 0, 0, 0);
+      int4 rec_3 = lv + 2 < lv_end ? level_rec[lv + 2] : make_int4(0, 0, 0, 0);
+      // static data and another column's theta: independent of the sweep's writes
+#define MYFM_REL_FETCH(REC, IDX, VAL, TH, LA, MU, ZZ)                                             \
+  {                                                                                                \
+    TH = a.theta[REC.x], ZZ = a.z[REC.x], LA = a.lambda[REC.w], MU = a.mu[REC.w];                  \
+    _Pragma("unroll") for (int k = 0; k < REL_REG; k++) {                                          \
+      const int p = REC.y + tt + NT * k;                                                           \
+      IDX[k] = p < REC.z ? a.Bt.idx[p] : -1;                                                       \
+      VAL[k] = p < REC.z ? a.Bt.val[p] : Real(0);                                                  \
+    }                                                                                              \
+  }
+      MYFM_REL_FETCH(rec_1, idx_1, val_1, theta_1, lam_1, mu_1, z_1)
+      if (lv + 1 < lv_end)
+        MYFM_REL_FETCH(rec_2, idx_2, val_2, theta_2, lam_2, mu_2, z_2)
+      for (int k_lv = lv; k_lv < lv_end; k_lv++) {
+        int idx[REL_REG];
+        Real val[REL_REG];
+#pragma unroll
+        for (int k = 0; k < REL_REG; k++)
+          idx[k] = idx_1[k], val[k] = val_1[k], idx_1[k] = idx_2[k], val_1[k] = val_2[k];
+        const int4 rec = rec_1;
+        const Real theta_old = theta_1, lam = lam_1, mu = mu_1, z = z_1;
+        theta_1 = theta_2, lam_1 = lam_2, mu_1 = mu_2, z_1 = z_2;
+        rec_1 = rec_2, rec_2 = rec_3;
+        if (k_lv + 3 < lv_end)
+          rec_3 = level_rec[k_lv + 3];
+        if (k_lv + 2 < lv_end)
+          MYFM_REL_FETCH(rec_2, idx_2, val_2, theta_2, lam_2, mu_2, z_2)
+        const int l = rec.x, b = rec.y, en = rec.z;
+        // A column holds a block row at most once, so its entries touch pairwise different cache
+        // slots: all loads of the column are issued before the first store (written one entry at a
+        // time the compiler would have to order every store before the next entry's loads).
+        Real qv[REL_REG], cardv[REL_REG], cv[REL_REG], cSv[REL_REG], ev[REL_REG], eqv[REL_REG], qSv[REL_REG];
+        Real sq = 0, lin = 0;
+#pragma unroll
+        for (int k = 0; k < REL_REG; k++)
+          if (idx[k] >= 0) {
+            const int sr = idx[k];
+            cardv[k] = m.card[sr], ev[k] = m.e[sr];
+            if (IS_V)
+              qv[k] = m.q[sr], cv[k] = m.c[sr], cSv[k] = m.c_S[sr], eqv[k] = m.e_q[sr], qSv[k] = m.q_S[sr];
+          }
+#pragma unroll
+        for (int k = 0; k < REL_REG; k++)
+          if (idx[k] >= 0) { // rel_pass1
+            const Real x = val[k];
+            if (IS_V) {
+              Real h_B = (qv[k] - x * theta_old);
+              Real h2 = h_B * h_B * cardv[k] + 2 * cv[k] * h_B + cSv[k];
+              h2 = x * x * h2;
+              sq += h2;
+              lin += (-ev[k] * h_B - eqv[k]) * x;
+            } else {
+              sq += (x * x) * cardv[k];
+              lin += (-x) * ev[k];
+            }
+          }
+        for (int p = b + tt + NT * REL_REG; p < en; p += NT) // the tail of a long column
+          rel_s_pass1<Real, IS_V>(m, a.Bt.idx[p], a.Bt.val[p], theta_old, sq, lin);
+        sq = warp_sum(sq);
+        lin = warp_sum(lin);
+        if (lane == 0)
+          s_red[2 * wid] = sq, s_red[2 * wid + 1] = lin;
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        sq = 0, lin = 0;
+#pragma unroll
+        for (int w = 0; w < REL_TEAM; w++) // warp partials in warp order: the same sums in every thread
+          sq += s_red[2 * w], lin += s_red[2 * w + 1];
+        const Real theta_new = rel_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
+        if (tt == 0) {
+          a.theta[l] = theta_new;
+          if (a.theta_t)
+            a.theta_t[static_cast<int64_t>(l) * a.t_stride] = theta_new;
+        }
+        const Real delta = theta_new - theta_old;
+#pragma unroll
+        for (int k = 0; k < REL_REG; k++)
+          if (idx[k] >= 0) { // rel_pass2
+            const Real x = val[k];
+            const int sr = idx[k];
+            if (IS_V) {
+              Real h_B = qv[k] - x * theta_old;
+              m.q[sr] = qv[k] + delta * x;
+              m.q_S[sr] = qSv[k] + delta * (theta_new + theta_old) * x * x;
+              m.e[sr] = ev[k] + x * delta * (h_B * cardv[k] + cv[k]);
+              m.e_q[sr] = eqv[k] + x * delta * (h_B * cv[k] + cSv[k]);
+            } else {
+              m.e[sr] = ev[k] + (x * cardv[k]) * delta;
+            }
+          }
+        for (int p = b + tt + NT * REL_REG; p < en; p += NT)
+          rel_s_pass2<Real, IS_V>(m, a.Bt.idx[p], a.Bt.val[p], theta_old, theta_new);
+        // the next column reads the caches this one wrote (and s_red is free again)
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+      }
+#undef MYFM_REL_FETCH
+    }
+    __syncthreads();
+    lv = lv_end;
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    a.cache.e[s] = m.e[s];
+    if (IS_V)
+      a.cache.q[s] = m.q[s], a.cache.q_S[s] = m.q_S[s], a.cache.e_q[s] = m.e_q[s];
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Small utilities
 // ----------------------------------------------------------------------------------------------

@@ -7,14 +7,12 @@ import argparse
 import os
 import sys
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402
 import myfm_b200  # noqa: E402
-from myfm_b200._myfm import ConfigBuilder, _TrainerHandle  # noqa: E402
+from myfm_b200._myfm import _TrainerHandle  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="ml10m")
@@ -23,12 +21,10 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--families", action="store_true", help="per-family CUDA-event times")
 args = ap.parse_args()
 
-X, y, group_shapes, rank = bench.make_workload(args.workload)
-cfg = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(group_shapes)), group_shapes))
-       .set_n_iter(args.sweeps).set_n_kept_samples(1).build())
+wl = bench.Workload(args.workload)
 with myfm_b200.engine_options(dtype=args.dtype):
-    t = _TrainerHandle(X, [], y, bench.CHAIN_SEED, cfg)
-    t.init_fm(rank, 0.1)
+    t = _TrainerHandle(wl.X, wl.blocks(), wl.y_engine, bench.CHAIN_SEED, wl.config(args.sweeps))
+    t.init_fm(wl.rank, 0.1)
 t.timed_steps(3)  # warm-up
 if args.families:
     t.set_profiling(True)
