@@ -52,9 +52,10 @@ extern "C" {
  *          the same seed.
  * PHILOX : the per-row latent draws of classification / ordered probit (FMTrainer.hpp:498-521,
  *          util.hpp:15-78) come from counter-based Philox4x32-10 streams on the device, keyed by
- *          (seed; row, sweep, attempt); the sweep's Gaussian / Gamma variates still follow the
+ *          (seed; global row, sweep, attempt); the sweep's Gaussian / Gamma variates still follow the
  *          mt19937 stream.  Statistically equivalent chain, no host involvement inside a sweep;
- *          regression chains are identical in both modes. */
+ *          regression chains are identical in both modes.  Row-sharded (world_size > 1)
+ *          classification / ordered probit needs this mode. */
 #define MYFM_RNG_MT19937 0
 #define MYFM_RNG_PHILOX 1
 
@@ -106,6 +107,12 @@ typedef struct myfm_engine_options {
    * consensus with myfm_level_schedule / myfm_level_relax).  NULL = compute from this shard. */
   const int32_t *column_level;
   int64_t n_column_level;
+  /* Global index of every training row of this shard, in the order the shard's rows are given
+   * (NULL: row_offset + i).  With MYFM_RNG_PHILOX the latent draw of a row is keyed by its GLOBAL
+   * index, so a row-sharded classification / ordered-probit chain draws what the single-GPU chain
+   * draws for the same row. */
+  const int64_t *row_ids;
+  int64_t n_row_ids;
 } myfm_engine_options_t;
 
 typedef struct myfm_trainer myfm_trainer_t;

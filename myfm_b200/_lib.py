@@ -79,6 +79,8 @@ class EngineOptions(C.Structure):
         ("nccl_unique_id", C.c_void_p),
         ("column_level", C.POINTER(C.c_int32)),
         ("n_column_level", C.c_int64),
+        ("row_ids", C.POINTER(C.c_int64)),
+        ("n_row_ids", C.c_int64),
     ]
 
 

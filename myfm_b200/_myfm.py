@@ -651,6 +651,12 @@ class _TrainerHandle:
         if opts.column_level is not None:
             levels = np.ascontiguousarray(opts.column_level, dtype=np.int32)
             eo.column_level, eo.n_column_level = _lib.ptr(levels, C.c_int32), levels.shape[0]
+        row_ids = None
+        if opts.row_ids is not None:
+            row_ids = np.ascontiguousarray(opts.row_ids, dtype=np.int64)
+            if row_ids.shape[0] != X.shape[0]:
+                raise ValueError("row_ids must have one entry per training row of this shard.")
+            eo.row_ids, eo.n_row_ids = _lib.ptr(row_ids, C.c_int64), row_ids.shape[0]
         cfg_struct = config._as_struct()
         h = C.c_void_p()
         _lib.check(_lib.lib().myfm_trainer_create(

@@ -419,6 +419,7 @@ template <typename Real> struct Trainer : TrainerBase {
   SweepPlan plan;
   std::vector<int> perm; // device row i holds the caller's row perm[i] (host_data.hpp)
   DevBuf<int> perm_dev;
+  DevBuf<int> latent_row; // device row -> global row index (the key of the row's Philox stream)
   DevBuf<SweepItem> items;
   DevBuf<int> seg_count;
   DevBuf<Real> seg_partial, seg_theta_old;
@@ -525,9 +526,9 @@ template <typename Real> struct Trainer : TrainerBase {
         throw std::invalid_argument("world_size > 1 needs the ncclUniqueId shared by all ranks.");
       if (n_rel > 0)
         throw std::runtime_error("relation blocks are not supported with row-sharded training yet.");
-      if (cfg.task_type != MYFM_TASK_REGRESSION)
-        throw std::runtime_error("row-sharded training supports regression only: the reference's latent draws "
-                                 "for classification / ordered probit consume the mt19937 stream row by row.");
+      if (cfg.task_type != MYFM_TASK_REGRESSION && !philox_latents)
+        throw std::runtime_error("row-sharded classification / ordered probit needs rng=philox: the reference's "
+                                 "latent draws consume the mt19937 stream row by row.");
     }
     const char *trace_env = std::getenv("MYFM_TRACE_SETUP");
     const bool trace = trace_env && trace_env[0] == '1';
@@ -612,6 +613,14 @@ template <typename Real> struct Trainer : TrainerBase {
       tick("tile path");
     }
     perm_dev.upload(perm, stream);
+    { // key of every device row's latent stream (PHILOX): its global row index
+      if (o.row_ids && o.n_row_ids != static_cast<int64_t>(perm.size()))
+        throw std::invalid_argument("row_ids must have one entry per training row of this shard.");
+      std::vector<int> key(perm.size());
+      for (size_t i = 0; i < perm.size(); i++)
+        key[i] = static_cast<int>(o.row_ids ? o.row_ids[perm[i]] : o.row_offset + perm[i]);
+      latent_row.upload(key, stream);
+    }
     items.upload(plan.items, stream);
     seg_count.upload(plan.seg_count, stream);
     if (world > 1) {
@@ -2077,7 +2086,7 @@ template <typename Real> struct Trainer : TrainerBase {
     if (philox_latents) {
       if (N) {
         k_latent_classification<Real><<<ceil_div(N, 256), 256, 0, stream>>>(
-            N, eq(), y.p, perm_dev.p, latent_seed, static_cast<uint32_t>(sweep_index + 1));
+            N, eq(), y.p, latent_row.p, latent_seed, static_cast<uint32_t>(sweep_index + 1));
         launched();
       }
       return;
@@ -2140,6 +2149,22 @@ template <typename Real> struct Trainer : TrainerBase {
           });
       max_class = std::max(max_class, cg.n_class);
     }
+    if (world > 1) { // the samplers of all ranks must walk the same Newton / MH steps
+      std::vector<int> sizes;
+      for (const CutGroup &cg : cut_groups)
+        sizes.push_back(cg.n_class), sizes.push_back(-cg.n_class);
+      sizes.push_back(static_cast<int>(cut_groups.size())), sizes.push_back(-static_cast<int>(cut_groups.size()));
+      DevBuf<int> buf(sizes.size());
+      std::vector<int> got(sizes.size());
+      buf.upload(sizes, stream);
+      NcclApi &nccl = NcclApi::get();
+      nccl.check(nccl.AllReduce(buf.p, buf.p, sizes.size(), ncclInt, ncclMax, comm, stream), "ncclAllReduce");
+      buf.download(got.data(), got.size(), stream);
+      MYFM_CUDA(cudaStreamSynchronize(stream));
+      for (size_t k = 0; k < sizes.size(); k += 2)
+        if (got[k] != sizes[k] || got[k + 1] != sizes[k + 1])
+          throw std::invalid_argument("cutpoint groups (their number and class counts) must be the same on every rank.");
+    }
     op_gamma.alloc(max_class);
     op_partial.alloc(static_cast<size_t>(max_class) * OP_BLOCKS_PER_CLASS * OP_TERMS);
     op_sums.alloc(static_cast<size_t>(max_class) * OP_TERMS);
@@ -2155,6 +2180,8 @@ template <typename Real> struct Trainer : TrainerBase {
     k_oprobit_finish<Real><<<ceil_div(Kc * OP_TERMS, 128), 128, 0, stream>>>(Kc, op_partial.p, op_sums.p);
     launched(2);
     MYFM_CUDA(cudaGetLastError());
+    if (world > 1) // OProbitSampler.hpp:389-463 sums over ALL rows: every rank gets the same totals
+      allreduce_sum(op_sums.p, static_cast<size_t>(Kc) * OP_TERMS);
     sums.resize(static_cast<size_t>(Kc) * OP_TERMS);
     op_sums.download(sums.data(), sums.size(), stream);
     MYFM_CUDA(cudaStreamSynchronize(stream));
@@ -2180,7 +2207,7 @@ template <typename Real> struct Trainer : TrainerBase {
         MYFM_CUDA(cudaStreamSynchronize(stream)); // lat_gamma may still be read by the previous group's kernel
         lat_gamma.upload(cg.cutpoints, stream);
         k_latent_ordered<Real><<<ceil_div(n_group, 256), 256, 0, stream>>>(
-            cg.n_class, cg.class_ptr.p, cg.class_rows.p, lat_gamma.p, eq(), perm_dev.p, latent_seed,
+            cg.n_class, cg.class_ptr.p, cg.class_rows.p, lat_gamma.p, eq(), latent_row.p, latent_seed,
             start ? 0u : static_cast<uint32_t>(sweep_index + 1));
         launched();
       }

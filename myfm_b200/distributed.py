@@ -124,7 +124,7 @@ class ShardContext:
             self._id_used = True
         with engine_options(world_size=self.world_size, rank=self.rank, row_offset=self.row_offset,
                             n_rows_global=self.n_rows_global, nccl_unique_id=uid,
-                            column_level=self.column_level, **kwargs):
+                            column_level=self.column_level, row_ids=self.rows, **kwargs):
             yield
 
 

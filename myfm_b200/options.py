@@ -35,6 +35,7 @@ class EngineOptions:
     n_rows_global: int = 0
     nccl_unique_id: Optional[bytes] = None
     column_level: Optional[object] = None  # int32 array: dependency level of every main-table column
+    row_ids: Optional[object] = None  # int64 array: global index of every row of this shard
 
 
 _current = EngineOptions()

@@ -111,3 +111,91 @@ def test_two_gpus_match_one(engine, dtype, exchange, no_field, partition, tmp_pa
     for r in range(2):
         e[np.load(tmp_path / f"rows_{r}.npy")] = np.load(tmp_path / f"e_{r}.npy")
     np.testing.assert_allclose(e, t.get_e(), rtol=tol, atol=tol)
+
+
+def _latent_data(task):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import fields_like
+
+    # three fields: rank-exclusive first field, a middle level on the general kernels, a gather-only last level
+    X, score, gs = fields_like(30011, [400, 30, 12], 3, seed=17, unit=True, noise=1.0)
+    if task == "classification":
+        y = np.where(score > np.median(score), 1.0, -1.0)
+    else:
+        y = np.digitize(score, np.quantile(score, [0.25, 0.5, 0.75])).astype(np.float64)
+    return X, y, gs
+
+
+def _latent_config(task, y, group_shapes, n_iter):
+    from myfm_b200._myfm import ConfigBuilder, TaskType
+
+    b = (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(len(group_shapes)), group_shapes))
+         .set_n_iter(n_iter).set_n_kept_samples(n_iter))
+    b.set_task_type(TaskType.CLASSIFICATION if task == "classification" else TaskType.ORDERED)
+    if task == "ordered":
+        b.set_cutpoint_groups([(4, np.arange(y.shape[0]))])
+    return b.build()
+
+
+def _latent_worker(rank: int, world: int, port: int, task: str, n_sweeps: int, out_dir: str) -> None:
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+
+    from myfm_b200 import distributed as mdist
+    from myfm_b200._myfm import _TrainerHandle
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        X, y, gs = _latent_data(task)
+        X_local, y_local, ctx = mdist.shard(X, y, partition="column")
+        with ctx.options(dtype="f64", device=rank, rng="philox"):
+            t = _TrainerHandle(X_local, [], y_local, 42, _latent_config(task, y_local, gs, n_sweeps))
+            t.init_fm(4, 0.1)
+        states, cuts = [], []
+        for _ in range(n_sweeps):
+            t.step(1)
+            states.append(_state(t))
+            if task == "ordered":
+                cuts.append(t.get_fm()[3][0])
+        np.save(os.path.join(out_dir, f"states_{rank}.npy"), np.stack(states))
+        if task == "ordered":
+            np.save(os.path.join(out_dir, f"cuts_{rank}.npy"), np.stack(cuts))
+            np.save(os.path.join(out_dir, f"accept_{rank}.npy"), np.asarray([t.mh_accept(0)]))
+        del t
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("task", ["classification", "ordered"])
+def test_two_gpus_latent_tasks_match_one(engine, task, tmp_path):
+    """Row-sharded probit classification / ordered probit (rng="philox"): the latent draw of a row is keyed by
+    its GLOBAL index and the cut-point sampler's row sums are all-reduced (OProbitSampler.hpp:389-463), so two
+    shards walk the chain of one GPU on the whole data (f64 1e-8; cut-points and MH acceptances included)."""
+    from myfm_b200 import _lib
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from myfm_b200._myfm import _TrainerHandle
+
+    n_sweeps = 4
+    mp.spawn(_latent_worker, args=(2, _free_port(), task, n_sweeps, str(tmp_path)), nprocs=2, join=True)
+    X, y, gs = _latent_data(task)
+    with engine.engine_options(dtype="f64", rng="philox"):
+        t = _TrainerHandle(X, [], y, 42, _latent_config(task, y, gs, n_sweeps))
+        t.init_fm(4, 0.1)
+    got = [np.load(tmp_path / f"states_{r}.npy") for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])
+    for it in range(n_sweeps):
+        t.step(1)
+        want = _state(t)
+        scale = np.maximum(np.abs(want), 1e-2)
+        assert np.max(np.abs(got[0][it] - want) / scale) < 1e-8, f"sweep {it}"
+        if task == "ordered":
+            np.testing.assert_allclose(np.load(tmp_path / "cuts_0.npy")[it], t.get_fm()[3][0], rtol=1e-8, atol=1e-10)
+    if task == "ordered":
+        assert int(np.load(tmp_path / "accept_0.npy")[0]) == t.mh_accept(0)
