@@ -131,6 +131,176 @@ class Workload:
         return dict(sweeps=sweeps, total=sweeps + K * q_init + e_refresh + misc)
 
 
+# ---- C5 (BASELINE.json configs[4]): 64 categorical fields x 31 250 categories, ordered probit, rank 64 ----
+C5_FIELDS, C5_CATS, C5_RANK, C5_ROWS = 64, 31_250, 64, 50_000_000
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser: a counter-based hash, so any rank can produce any row's data."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def c5_field_column(rows: np.ndarray, field: int) -> np.ndarray:
+    """Category (0 .. C5_CATS-1) of `field` for the global rows `rows`."""
+    h = _mix64(rows.astype(np.uint64) * np.uint64(C5_FIELDS) + np.uint64(field) + np.uint64(DATA_SEED) * np.uint64(1 << 40))
+    return (h % np.uint64(C5_CATS)).astype(np.int32)
+
+
+class C5Shard:
+    """This rank's rows of the C5 table, generated locally (no rank materialises the 3.2 G non-zeros):
+    rows are dealt out by their first-field category (rank-exclusive first field), the other 63 fields,
+    the planted score and the five ordinal classes come from counter-based hashes of the global row."""
+
+    def __init__(self, n_rows: int, rank: int, world: int):
+        from myfm_b200 import distributed as mdist
+
+        self.n_rows_global, self.rank_id, self.world = n_rows, rank, world
+        all_rows = np.arange(n_rows, dtype=np.int64)
+        first = c5_field_column(all_rows, 0)
+        self.rows = all_rows[mdist.partition_by_key(first, C5_CATS, world) == rank] if world > 1 else all_rows
+        del all_rows, first
+        n = self.rows.shape[0]
+        cols = np.empty((n, C5_FIELDS), dtype=np.int32)
+        rng = np.random.default_rng(DATA_SEED)
+        w_planted = rng.normal(0, 0.25, C5_FIELDS * C5_CATS).astype(np.float32)
+        score = np.zeros(n, dtype=np.float32)
+        for f in range(C5_FIELDS):
+            c = c5_field_column(self.rows, f)
+            cols[:, f] = f * C5_CATS + c
+            score += w_planted[f * C5_CATS + c]
+        u = (_mix64(self.rows.astype(np.uint64) + np.uint64(1 << 50)) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+        v = (_mix64(self.rows.astype(np.uint64) + np.uint64(1 << 51)) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+        score = score + (np.sqrt(-2 * np.log(u + 1e-300)) * np.cos(2 * np.pi * v)).astype(np.float32)
+        # the score is N(0, 64 * 0.25^2 + 1) = N(0, 5): quintiles of that normal
+        cuts = np.sqrt(5.0) * np.asarray([-0.8416, -0.2533, 0.2533, 0.8416])
+        self.y = np.digitize(score, cuts).astype(np.float64)
+        import scipy.sparse as sps
+
+        indptr = np.arange(0, C5_FIELDS * n + 1, C5_FIELDS, dtype=np.int64)
+        self.X = sps.csr_matrix((np.ones(C5_FIELDS * n, dtype=np.float64), cols.ravel(), indptr),
+                                shape=(n, C5_FIELDS * C5_CATS))
+        self.group_shapes = [C5_CATS] * C5_FIELDS
+        self.nnz_global = n_rows * C5_FIELDS
+
+    def config(self, n_iter: int):
+        from myfm_b200._myfm import ConfigBuilder, TaskType
+
+        return (ConfigBuilder().set_mu_0(0.0).set_group_index(np.repeat(np.arange(C5_FIELDS), C5_CATS))
+                .set_n_iter(n_iter).set_n_kept_samples(1).set_task_type(TaskType.ORDERED)
+                .set_cutpoint_groups([(N_CLASSES, np.arange(self.X.shape[0]))]).build())
+
+
+def run_c5(args):
+    """--workload c5: ordered probit on 64 fields x 31 250 categories, rank 64, rows sharded by their first
+    field, Philox latent draws (statistical parity: SURVEY.md section 8d)."""
+    import myfm_b200
+    from myfm_b200._myfm import _TrainerHandle
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_id = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    n_rows = args.rows or C5_ROWS
+    t0 = time.perf_counter()
+    shard = C5Shard(n_rows, rank_id, world)
+    t_gen = time.perf_counter() - t0
+    n_total = args.steps + args.warmup
+    if dist is not None:
+        from myfm_b200 import distributed as mdist
+
+        ctx = mdist.context(shard.X, 0, n_rows)
+        ctx.rows = shard.rows
+        options = lambda: ctx.options(dtype=args.dtype, device=local, rng="philox")  # noqa: E731
+    else:
+        options = lambda: myfm_b200.engine_options(dtype=args.dtype, device=local, rng="philox")  # noqa: E731
+    t0 = time.perf_counter()
+    with options():
+        trainer = _TrainerHandle(shard.X, [], shard.y, CHAIN_SEED, shard.config(n_total))
+        trainer.init_fm(C5_RANK, 0.1)
+    t_setup = time.perf_counter() - t0
+    trainer.step(args.warmup)
+    trainer.sync()
+    launches0 = trainer.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    ms = trainer.timed_steps(args.steps)
+    # end to end at the handle level: one sweep, then the sweep's hyper-parameters and cut-points to the host
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        trainer.step(1)
+        hyper = trainer.get_hyper()
+        cut = trainer.get_fm()[3][0] if False else None  # (the cut-points live on the host already)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([ms, e2e_s, t_setup, t_gen], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, t_setup, t_gen = (float(v) for v in t.tolist())
+    clocks = sampler.stop()
+    launches = trainer.launch_count() - launches0
+    sweep_path = trainer.sweep_path()
+    accept = trainer.mh_accept(0)
+    cutpoints = trainer.get_fm()[3][0].tolist()
+    del trainer
+    if rank_id != 0:
+        dist.destroy_process_group()
+        return
+    it_per_s = args.steps / (ms / 1e3)
+    b = 4 if args.dtype == "f32" else 8
+    nnz, K = n_rows * C5_FIELDS, C5_RANK
+    # SURVEY.md section 8(d): B_iter = K (32 nnz + 8 N) + 24 nnz + 24 N for f32 (whole job)
+    v_sweep, q_init = (4 + b) * nnz + 4 * b * nnz, (4 + b) * nnz + 4 * n_rows + b * n_rows
+    total_bytes = K * (v_sweep + q_init) + (4 + b) * nnz + 2 * b * nnz + (4 + b) * nnz + 4 * n_rows + 2 * b * n_rows
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    achieved = total_bytes * it_per_s / 1e9 / world
+    path_name, kernel_desc = SWEEP_PATHS.get(sweep_path, (str(sweep_path), "?"))
+    line = {
+        "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"c5-shaped synthetic: {n_rows} rows x {C5_FIELDS} categorical fields x {C5_CATS} "
+                               f"categories (D = {C5_FIELDS * C5_CATS}), {C5_FIELDS} nnz per row (nnz = {nnz}), rank {K}, "
+                               f"ordered probit with {N_CLASSES} classes, group_shapes=[{C5_CATS}] * {C5_FIELDS}; rows "
+                               f"generated per shard from counter-based hashes",
+                   "rank": K, "rows": n_rows, "nnz": nnz, "task": "ordered",
+                   "rng": "philox latent draws on the device (statistical parity); Gaussian / Gamma variates from the "
+                          "device-side mt19937 stream",
+                   "parallelism": (f"rows dealt out over {world} GPUs by their first-field category (that field needs no "
+                                   f"exchange); the other 63 dependency levels: column statistics all-reduced per level "
+                                   f"(ncclAllReduce / peer memory); cut-point row sums all-reduced per Newton / MH evaluation")
+                   if world > 1 else "single GPU"},
+        "sweep_path": path_name, "nnz_rank_per_sec": it_per_s * nnz * K,
+        "e2e": {"value": args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": int((2 + 2 * C5_FIELDS + 2 * C5_FIELDS * K) * b),
+                "setup_s": t_setup, "generate_s": t_gen,
+                "note": "trainer handle: one sweep, then the sweep's hyper-parameters on the host (what "
+                        "create_train_fm does per iteration); the one-off upload / preparation is setup_s"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": kernel_desc + "; middle levels: k_level_dist / k_level_sweep",
+                     "algorithmic_bytes_per_step": total_bytes, "note": "whole sweep, per GPU (SURVEY.md section 8d: "
+                     "832 GB per iteration and GPU at 50 M rows on 8 GPUs)"},
+        "cutpoints_last": cutpoints, "mh_accept": int(accept), "alpha_last": hyper.alpha,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -502,7 +672,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ml10m", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--rows", type=int, default=None, help="c5: total training rows (default 50 000 000)")
     ap.add_argument("--task", default="regression", choices=["regression", "classification", "ordered"])
     ap.add_argument("--rank", type=int, default=None, help="override the workload's rank")
     ap.add_argument("--rng", default="mt19937", choices=["mt19937", "philox"])
@@ -510,7 +681,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "c5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "c5 is sized for 8 GPUs; the CPU oracle is not run on it"}))
+        else:
+            run_c5(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -230,6 +230,32 @@ int myfm_predict_samples_mean(const myfm_dataset_t *d, int32_t task_type, int32_
  * by per-iteration callbacks (src/myfm/utils/callbacks/libfm.py:82-113). */
 int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, double *out);
 
+/* ---- per-iteration evaluation callbacks on the device ------------------------------------------
+ * The reference's LibFM-style callbacks (src/myfm/utils/callbacks/libfm.py:57-262) call
+ * fm.predict_score / fm.oprobit_predict_proba on a held-out set every iteration and keep running
+ * means in numpy.  An evaluator keeps the test matrix (a myfm_dataset_t, not owned), the targets,
+ * both running sums (all sweeps; all but the first five) and the metric reductions on the device.
+ * task_type REGRESSION: clip_min / clip_max clip the running means (NaN = no clipping);
+ * CLASSIFICATION: y_test in {0, 1}, eps clips the running means to [eps, 1 - eps] (eps < 0: none);
+ * ORDERED: y_test = class index in [0, n_class), eps is the floor of the picked probability.
+ * myfm_evaluator_step runs one callback step with the trainer's CURRENT sample and writes 9 sums
+ * over the test rows, in the order (running mean, this sweep, mean of all but the first five):
+ *   REGRESSION      [0..2] squared error
+ *   CLASSIFICATION  [0..2] negative log-likelihood, [3..5] correct decisions
+ *   ORDERED         [0..2] negative log-likelihood, [3..5] correct arg-max, [6..8] squared error of
+ *                   the expected class
+ * (the third of each group is 0 while iteration < 5).  cutpoints: the sample's cut-points
+ * (ORDERED, n_cpt = n_class - 1).  myfm_evaluator_get_sums copies the running sums
+ * ([n_test x width], width = 1 or n_class; either pointer may be NULL). */
+typedef struct myfm_evaluator myfm_evaluator_t;
+int myfm_evaluator_create(myfm_evaluator_t **out, const myfm_dataset_t *d, const double *y_test,
+                          int64_t n_test, int32_t task_type, int32_t n_class, double clip_min,
+                          double clip_max, double eps);
+void myfm_evaluator_destroy(myfm_evaluator_t *e);
+int myfm_evaluator_step(myfm_evaluator_t *e, myfm_trainer_t *t, int32_t iteration,
+                        const double *cutpoints, int32_t n_cpt, double *terms);
+int myfm_evaluator_get_sums(myfm_evaluator_t *e, double *sum, double *late);
+
 /* ---- host-side pieces that run without a GPU (exercised by the CPU test-suite) -------------- */
 
 /* The engine's MT19937 variate stream for one regression sweep layout: fills `out` with the

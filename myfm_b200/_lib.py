@@ -97,6 +97,7 @@ EXPORTS = [
     "myfm_trainer_snapshot", "myfm_sample_destroy", "myfm_sample_get", "myfm_predict_samples_mean",
     "myfm_level_schedule", "myfm_level_relax", "myfm_host_transpose", "myfm_set_host_threads", "myfm_nccl_unique_id",
     "myfm_mt_jump_taps",
+    "myfm_evaluator_create", "myfm_evaluator_destroy", "myfm_evaluator_step", "myfm_evaluator_get_sums",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -116,6 +117,12 @@ def lib() -> C.CDLL:
         L.myfm_trainer_destroy.restype = None
         L.myfm_dataset_destroy.restype = None
         L.myfm_sample_destroy.restype = None
+        L.myfm_evaluator_destroy.restype = None
+        L.myfm_evaluator_destroy.argtypes = [C.c_void_p]
+        L.myfm_evaluator_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                            C.c_double, C.c_double, C.c_double]
+        L.myfm_evaluator_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.myfm_evaluator_get_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.myfm_sample_destroy.argtypes = [C.c_void_p]
         L.myfm_predict_score.argtypes = [
             C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]

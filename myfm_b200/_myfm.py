@@ -19,7 +19,7 @@ from scipy import sparse as sps
 from scipy import special
 
 from . import _lib
-from .options import get_options
+from .options import engine_options, get_options
 
 __all__ = [
     "TaskType", "FMLearningConfig", "ConfigBuilder", "RelationBlock", "FM", "FMHyperParameters",
@@ -416,6 +416,47 @@ class _LiveFM(FM):
 
     def __reduce__(self):
         return (FM, self.freeze().__getstate__())
+
+
+class _DeviceEvaluator:
+    """Device half of the LibFM-style callbacks (myfm_evaluator_*): the held-out matrix, the running sums of
+    the per-sweep predictions and the metric reductions stay in HBM; `step` returns nine sums."""
+
+    def __init__(self, live: "_LiveFM", X, relations: Sequence[RelationBlock], y_test: np.ndarray, task: "TaskType",
+                 n_class: int = 0, clip_min: Optional[float] = None, clip_max: Optional[float] = None,
+                 eps: Optional[float] = None) -> None:
+        self._h = None
+        trainer = live._trainer
+        with engine_options(dtype=trainer.dtype, device=trainer.device):
+            self._ds = _device_dataset(_as_csr(X), list(relations))  # keeps the upload alive
+        y = np.ascontiguousarray(y_test, dtype=np.float64)
+        nan = float("nan")
+        h = C.c_void_p()
+        _lib.check(_lib.lib().myfm_evaluator_create(
+            C.byref(h), self._ds._h, _lib.vptr(y), C.c_int64(y.shape[0]), C.c_int32(int(task)), C.c_int32(int(n_class)),
+            C.c_double(nan if clip_min is None else clip_min), C.c_double(nan if clip_max is None else clip_max),
+            C.c_double(-1.0 if eps is None else eps)))
+        self._h = h
+        self.n, self.width = y.shape[0], (int(n_class) if task == TaskType.ORDERED else 1)
+
+    def step(self, live: "_LiveFM", iteration: int, cutpoints: Optional[np.ndarray] = None) -> np.ndarray:
+        terms = np.zeros(9, dtype=np.float64)
+        cp = None if cutpoints is None else np.ascontiguousarray(cutpoints, dtype=np.float64)
+        _lib.check(_lib.lib().myfm_evaluator_step(
+            self._h, live._trainer._h, C.c_int32(int(iteration)), None if cp is None else _lib.vptr(cp),
+            C.c_int32(0 if cp is None else cp.shape[0]), _lib.vptr(terms)))
+        return terms
+
+    def sums(self) -> Tuple[np.ndarray, np.ndarray]:
+        shape = (self.n,) if self.width == 1 else (self.n, self.width)
+        total, late = np.zeros(shape, dtype=np.float64), np.zeros(shape, dtype=np.float64)
+        _lib.check(_lib.lib().myfm_evaluator_get_sums(self._h, _lib.vptr(total), _lib.vptr(late)))
+        return total, late
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.lib().myfm_evaluator_destroy(self._h)
+            self._h = None
 
 
 class _DeviceFM(FM):

@@ -9,6 +9,7 @@
 #include "field_sweep.cuh"
 #include "tile_sweep.cuh"
 #include "latent_device.cuh"
+#include "eval_device.cuh"
 #include "mt_device.cuh"
 #include "mt_jump.hpp"
 #include "oprobit.cuh"
@@ -151,6 +152,15 @@ struct DatasetBase {
   int dtype = MYFM_DTYPE_F32;
   int device = 0;
   int64_t n_rows = 0, dim_main = 0, dim_all = 0;
+};
+
+// Running state of a per-iteration evaluation callback on the device (eval_device.cuh).
+struct EvalState {
+  DatasetBase *dataset = nullptr; // not owned
+  int task = MYFM_TASK_REGRESSION, width = 1, n_samples = 0;
+  int64_t n = 0;
+  double clip_min = 0, clip_max = 0, eps = -1;
+  DevBuf<double> sum, late, y, cutp, partial, out;
 };
 
 template <typename Real> struct Dataset : DatasetBase {
@@ -391,6 +401,7 @@ struct TrainerBase {
   virtual void kernel_ms(int family, double *ms, int64_t *launches) = 0;
   virtual void set_profiling(bool on) = 0;
   virtual void predict_score(DatasetBase *d, double *out) = 0;
+  virtual void evaluate(EvalState &ev, int iteration, const double *cutpoints, int n_cpt, double *terms) = 0;
   virtual int64_t get_variates(double *out, int64_t capacity) = 0;
   int dtype = MYFM_DTYPE_F32;
 };
@@ -593,6 +604,7 @@ template <typename Real> struct Trainer : TrainerBase {
       tick("dependency levels");
       perm = primary_row_order(Xth0, level, n_levels, &primary);
       Xh = permute_rows(Xh, perm);
+      Xth0 = HostCs<Real>(); // not needed any more (hundreds of MB to GB on the large configurations)
       tick("row order + permute");
       main_unit = std::all_of(Xh.val.begin(), Xh.val.end(), [](Real v) { return v == Real(1); });
       main_row_len = Xh.n_major ? Xh.ptr[1] - Xh.ptr[0] : 0;
@@ -2592,6 +2604,41 @@ template <typename Real> struct Trainer : TrainerBase {
     sync();
     timer.enabled = on;
   }
+  // One step of a LibFM-style callback (libfm.py:44-54, :82-113, :150-182, :226-262) with the live sample:
+  // forward pass, link, running sums and metric terms on the device; EVAL_TERMS sums come back.
+  void evaluate(EvalState &ev, int iteration, const double *cutpoints, int n_cpt, double *terms) override {
+    require_fm();
+    if (ev.dataset->dtype != dtype)
+      throw std::invalid_argument("dataset and trainer use different compute dtypes.");
+    auto *d = static_cast<Dataset<Real> *>(ev.dataset);
+    d->check_dim(D_all);
+    if (ev.task == MYFM_TASK_ORDERED && n_cpt + 1 != ev.width)
+      throw std::invalid_argument("the number of cut-points does not match the evaluator's class count.");
+    MYFM_CUDA(cudaSetDevice(device));
+    MYFM_CUDA(cudaStreamSynchronize(stream)); // the sample must be final before another stream reads it
+    if (d->score.n < static_cast<size_t>(d->n_rows))
+      d->score.alloc(d->n_rows);
+    d->predict(w.p, Vt.p, K, hv().w0, nullptr, d->score.p);
+    ev.n_samples++;
+    EvalArgs a;
+    a.n = static_cast<int>(ev.n), a.width = ev.width, a.task = ev.task, a.iteration = iteration;
+    a.n_samples = ev.n_samples, a.burn_in = 5;
+    a.clip_min = ev.clip_min, a.clip_max = ev.clip_max, a.eps = ev.eps;
+    a.sum = ev.sum.p, a.late = ev.late.p, a.y = ev.y.p, a.cutpoints = ev.cutp.p, a.partial = ev.partial.p;
+    if (ev.task == MYFM_TASK_ORDERED && n_cpt > 0)
+      ev.cutp.upload(cutpoints, n_cpt, d->stream);
+    if (ev.n) {
+      k_eval<Real><<<EVAL_BLOCKS, EVAL_THREADS, 0, d->stream>>>(a, d->score.p);
+      k_eval_finish<<<1, 32, 0, d->stream>>>(EVAL_BLOCKS, ev.partial.p, ev.out.p);
+      d->count(2);
+      MYFM_CUDA(cudaGetLastError());
+      ev.out.download(terms, EVAL_TERMS, d->stream);
+    } else {
+      std::fill(terms, terms + EVAL_TERMS, 0.0);
+    }
+    MYFM_CUDA(cudaStreamSynchronize(d->stream));
+  }
+
   void predict_score(DatasetBase *db, double *out) override {
     require_fm();
     if (db->dtype != dtype)
@@ -3029,6 +3076,58 @@ int myfm_trainer_predict_score(myfm_trainer_t *t, const myfm_dataset_t *d, doubl
   MYFM_API_BEGIN
   require(t, "trainer"), require(d, "dataset");
   t->impl->predict_score(d->impl.get(), out);
+  MYFM_API_END
+}
+
+struct myfm_evaluator {
+  EvalState state;
+};
+
+int myfm_evaluator_create(myfm_evaluator_t **out, const myfm_dataset_t *d, const double *y_test, int64_t n_test,
+                          int32_t task_type, int32_t n_class, double clip_min, double clip_max, double eps) {
+  MYFM_API_BEGIN
+  require(out, "out"), require(d, "dataset");
+  if (n_test > 0)
+    require(y_test, "y_test");
+  if (n_test != d->impl->n_rows)
+    throw std::invalid_argument("y_test must have one entry per row of the dataset.");
+  if (task_type == MYFM_TASK_ORDERED && n_class < 2)
+    throw std::invalid_argument("ordered probit needs at least two classes.");
+  MYFM_CUDA(cudaSetDevice(d->impl->device));
+  auto holder = std::make_unique<myfm_evaluator>();
+  EvalState &ev = holder->state;
+  ev.dataset = d->impl.get();
+  ev.task = task_type, ev.width = task_type == MYFM_TASK_ORDERED ? n_class : 1, ev.n = n_test;
+  ev.clip_min = clip_min, ev.clip_max = clip_max, ev.eps = eps;
+  const size_t cells = static_cast<size_t>(n_test) * ev.width;
+  ev.sum.alloc(cells), ev.late.alloc(cells);
+  ev.sum.zero(), ev.late.zero();
+  ev.y.upload(y_test, n_test);
+  ev.cutp.alloc(std::max(1, ev.width));
+  ev.partial.alloc(static_cast<size_t>(EVAL_BLOCKS) * EVAL_TERMS), ev.out.alloc(EVAL_TERMS);
+  MYFM_CUDA(cudaDeviceSynchronize());
+  *out = holder.release();
+  MYFM_API_END
+}
+void myfm_evaluator_destroy(myfm_evaluator_t *e) { delete e; }
+int myfm_evaluator_step(myfm_evaluator_t *e, myfm_trainer_t *t, int32_t iteration, const double *cutpoints,
+                        int32_t n_cpt, double *terms) {
+  MYFM_API_BEGIN
+  require(e, "evaluator"), require(t, "trainer"), require(terms, "terms");
+  if (n_cpt > 0)
+    require(cutpoints, "cutpoints");
+  t->impl->evaluate(e->state, iteration, cutpoints, n_cpt, terms);
+  MYFM_API_END
+}
+int myfm_evaluator_get_sums(myfm_evaluator_t *e, double *sum, double *late) {
+  MYFM_API_BEGIN
+  require(e, "evaluator");
+  MYFM_CUDA(cudaSetDevice(e->state.dataset->device));
+  const size_t cells = static_cast<size_t>(e->state.n) * e->state.width;
+  if (sum && cells)
+    MYFM_CUDA(cudaMemcpy(sum, e->state.sum.p, cells * sizeof(double), cudaMemcpyDeviceToHost));
+  if (late && cells)
+    MYFM_CUDA(cudaMemcpy(late, e->state.late.p, cells * sizeof(double), cudaMemcpyDeviceToHost));
   MYFM_API_END
 }
 

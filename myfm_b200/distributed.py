@@ -138,6 +138,19 @@ def context(X_local, row_offset: int, n_rows_global: int, group=None, with_nccl:
     return ShardContext(world, rank, int(row_offset), int(n_rows_global), uid, levels, group)
 
 
+def partition_by_key(key: np.ndarray, n_keys: int, world_size: int) -> np.ndarray:
+    """Rank of every row given the row's key in [0, n_keys) (its first-field column): keys are dealt
+    out in serpentine order of their row counts (see `column_partition`)."""
+    counts = np.bincount(key, minlength=n_keys)
+    order = np.argsort(-counts, kind="stable")
+    pos = np.arange(order.shape[0])
+    lap, lane = pos // world_size, pos % world_size
+    rank_sorted = np.where(lap % 2 == 0, lane, world_size - 1 - lane)
+    rank_of_key = np.empty(order.shape[0], dtype=np.int32)
+    rank_of_key[order] = rank_sorted
+    return rank_of_key[key]
+
+
 def column_partition(X: sps.csr_matrix, world_size: int) -> np.ndarray:
     """Rank of every row when rows are dealt out by their FIRST column (for one-hot / categorical
     tables: by the category of the first field, e.g. by user).  Every first-field column then has

@@ -2,9 +2,11 @@
 
 Every sweep the callback scores the held-out set with the CURRENT sample, keeps running means
 (over all sweeps, and over all but the first five) and appends the metrics to ``result_trace``.
-The live `fm` handed in by the engine predicts from its device-resident weights against a test
-matrix that stays cached in HBM, so the per-iteration cost is one fused forward kernel plus the
-copy of the scores.
+When the `fm` handed in is the engine's live, device-resident sample (what `fit()` passes), the
+whole step runs on the device (`_myfm._DeviceEvaluator` -> csrc/eval_device.cuh): forward pass, link,
+both running sums and the metric reductions against a test matrix that stays in HBM; nine scalars
+come back per sweep, and `predictions` / `prediction_all_but_5` are fetched only when read.  A plain
+host `FM` takes the numpy path of the reference.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 from scipy import sparse as sps
 
-from ..._myfm import FM, FMHyperParameters, LearningHistory, RelationBlock
+from ..._myfm import FM, FMHyperParameters, LearningHistory, RelationBlock, TaskType, _DeviceEvaluator, _LiveFM
 from ...base import REAL, ArrayLike, check_data_consistency, std_cdf
 
 _BURN_IN = 5
@@ -46,6 +48,41 @@ class LibFMLikeCallbackBase(ABC):
             self.prediction_all_but_5 += this
             late = self.prediction_all_but_5 / (i + 1 - _BURN_IN)
         return mean, late
+
+    # ---- device path -----------------------------------------------------------------------------
+    _device: Optional[_DeviceEvaluator] = None
+    _host_predictions: np.ndarray
+    _host_all_but_5: np.ndarray
+
+    def _device_kwargs(self) -> Dict:
+        raise NotImplementedError
+
+    def _device_terms(self, i: int, fm: FM, cutpoints=None) -> Optional[np.ndarray]:
+        """The nine metric sums of this step from the device, or None when `fm` is a host object (or a host
+        step has already been taken: the running sums then live in numpy)."""
+        if not isinstance(fm, _LiveFM) or (self._device is None and self.n_samples > 0):
+            return None
+        if self._device is None:
+            self._device = _DeviceEvaluator(fm, self.X_test, self.X_rel_test, self.y_test, **self._device_kwargs())
+        self.n_samples += 1
+        return self._device.step(fm, i, cutpoints)
+
+    # the running sums live on the device while the device path is in use; reading them copies them
+    @property
+    def predictions(self) -> np.ndarray:
+        return self._device.sums()[0] if self._device is not None else self._host_predictions
+
+    @predictions.setter
+    def predictions(self, value: np.ndarray) -> None:
+        self._host_predictions = value
+
+    @property
+    def prediction_all_but_5(self) -> np.ndarray:
+        return self._device.sums()[1] if self._device is not None else self._host_all_but_5
+
+    @prediction_all_but_5.setter
+    def prediction_all_but_5(self, value: np.ndarray) -> None:
+        self._host_all_but_5 = value
 
     @abstractmethod
     def _measure_score(self, i: int, fm: FM, hyper: FMHyperParameters) -> Tuple[str, Dict[str, float]]:
@@ -80,15 +117,24 @@ class RegressionCallback(LibFMLikeCallbackBase):
     def _rmse(self, pred: np.ndarray) -> float:
         return float(((self.y_test - pred) ** 2).mean() ** 0.5)
 
+    def _device_kwargs(self):
+        return dict(task=TaskType.REGRESSION, clip_min=self.clip_min, clip_max=self.clip_max)
+
     def _measure_score(self, i, fm, hyper):
-        score = fm.predict_score(self.X_test, self.X_rel_test)
-        mean, late = self._accumulate(i, score)
-        self.clip_value(mean)
-        rmse_late = float("nan")
-        if late is not None:
-            self.clip_value(late)
-            rmse_late = self._rmse(late)
-        rmse, rmse_this = self._rmse(mean), self._rmse(score)
+        terms = self._device_terms(i, fm)
+        if terms is not None:
+            n = max(1, self.n_test_data)
+            rmse, rmse_this = (terms[0] / n) ** 0.5, (terms[1] / n) ** 0.5
+            rmse_late = (terms[2] / n) ** 0.5 if i >= _BURN_IN else float("nan")
+        else:
+            score = fm.predict_score(self.X_test, self.X_rel_test)
+            mean, late = self._accumulate(i, score)
+            self.clip_value(mean)
+            rmse_late = float("nan")
+            if late is not None:
+                self.clip_value(late)
+                rmse_late = self._rmse(late)
+            rmse, rmse_this = self._rmse(mean), self._rmse(score)
         description = "alpha={0:.4f}, rmse_mean={1:.4f}, rmse_this={2:.4f}, rmse_all_but_5={3:.4f}".format(
             hyper.alpha, rmse, rmse_this, rmse_late)
         return description, OrderedDict(
@@ -115,16 +161,25 @@ class ClassificationCallback(LibFMLikeCallbackBase):
     def _accuracy(self, p: np.ndarray) -> float:
         return float((self.y_test == (p >= 0.5)).mean())
 
+    def _device_kwargs(self):
+        return dict(task=TaskType.CLASSIFICATION, eps=self.eps)
+
     def _measure_score(self, i, fm, hyper):
-        prob_this = std_cdf(fm.predict_score(self.X_test, self.X_rel_test))
-        mean, late = self._accumulate(i, prob_this)
-        self.clip_value(mean)
-        ll_late = acc_late = float("nan")
-        if late is not None:
-            self.clip_value(late)
-            ll_late, acc_late = self._log_loss(late), self._accuracy(late)
-        ll, acc = self._log_loss(mean), self._accuracy(mean)
-        ll_this, acc_this = self._log_loss(prob_this), self._accuracy(prob_this)
+        terms = self._device_terms(i, fm)
+        if terms is not None:
+            n = max(1, self.n_test_data)
+            ll, ll_this, acc, acc_this = terms[0], terms[1], terms[3] / n, terms[4] / n
+            ll_late, acc_late = (terms[2], terms[5] / n) if i >= _BURN_IN else (float("nan"), float("nan"))
+        else:
+            prob_this = std_cdf(fm.predict_score(self.X_test, self.X_rel_test))
+            mean, late = self._accumulate(i, prob_this)
+            self.clip_value(mean)
+            ll_late = acc_late = float("nan")
+            if late is not None:
+                self.clip_value(late)
+                ll_late, acc_late = self._log_loss(late), self._accuracy(late)
+            ll, acc = self._log_loss(mean), self._accuracy(mean)
+            ll_this, acc_this = self._log_loss(prob_this), self._accuracy(prob_this)
         description = "ll_mean={0:.4f}, ll_this={1:.4f}, ll_all_but_5={2:.4f}".format(ll, ll_this, ll_late)
         return description, OrderedDict([
             ("log_loss", ll), ("log_loss_this", ll_this), ("log_loss_all_but_5", ll_late),
@@ -154,14 +209,26 @@ class OrderedProbitCallback(LibFMLikeCallbackBase):
     def _rmse(self, p: np.ndarray) -> float:
         return float(((self.y_test - p.dot(np.arange(self.n_class))) ** 2).mean()) ** 0.5
 
+    def _device_kwargs(self):
+        return dict(task=TaskType.ORDERED, n_class=self.n_class, eps=self.eps)
+
     def _measure_score(self, i, fm, hyper):
-        prob_this = fm.oprobit_predict_proba(self.X_test, self.X_rel_test, 0)
-        mean, late = self._accumulate(i, prob_this)
-        ll_late = acc_late = rmse_late = float("nan")
-        if late is not None:
-            ll_late, acc_late, rmse_late = self._log_loss(late), self._accuracy(late), self._rmse(late)
-        ll, acc, rmse = self._log_loss(mean), self._accuracy(mean), self._rmse(mean)
-        ll_this, acc_this, rmse_this = self._log_loss(prob_this), self._accuracy(prob_this), self._rmse(prob_this)
+        terms = self._device_terms(i, fm, fm.cutpoints[0]) if isinstance(fm, _LiveFM) else None
+        if terms is not None:
+            n = max(1, self.n_test_data)
+            ll, ll_this, acc, acc_this = terms[0], terms[1], terms[3] / n, terms[4] / n
+            rmse, rmse_this = (terms[6] / n) ** 0.5, (terms[7] / n) ** 0.5
+            ll_late = acc_late = rmse_late = float("nan")
+            if i >= _BURN_IN:
+                ll_late, acc_late, rmse_late = terms[2], terms[5] / n, (terms[8] / n) ** 0.5
+        else:
+            prob_this = fm.oprobit_predict_proba(self.X_test, self.X_rel_test, 0)
+            mean, late = self._accumulate(i, prob_this)
+            ll_late = acc_late = rmse_late = float("nan")
+            if late is not None:
+                ll_late, acc_late, rmse_late = self._log_loss(late), self._accuracy(late), self._rmse(late)
+            ll, acc, rmse = self._log_loss(mean), self._accuracy(mean), self._rmse(mean)
+            ll_this, acc_this, rmse_this = self._log_loss(prob_this), self._accuracy(prob_this), self._rmse(prob_this)
         description = "ll_mean={0:.4f}, ll_this={1:.4f}, ll_all_but_5={2:.4f}".format(ll, ll_this, ll_late)
         return description, OrderedDict([
             ("log_loss", ll), ("log_loss_this", ll_this), ("log_loss_all_but_5", ll_late),
