@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmyfm_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "field_sweep.cuh", "tile_sweep.cuh", "latent_device.cuh", "eval_device.cuh", "host_data.hpp", "rng.hpp", "mt_device.cuh", "mt_jump.hpp", "oprobit.cuh",
+HEADERS = ["common.cuh", "kernels.cuh", "field_sweep.cuh", "tile_sweep.cuh", "latent_device.cuh", "eval_device.cuh", "prep_device.cuh", "host_data.hpp", "rng.hpp", "mt_device.cuh", "mt_jump.hpp", "oprobit.cuh",
            "../../include/myfm_b200.h"]
 
 NVCC_FLAGS = [

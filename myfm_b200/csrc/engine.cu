@@ -10,6 +10,7 @@
 #include "tile_sweep.cuh"
 #include "latent_device.cuh"
 #include "eval_device.cuh"
+#include "prep_device.cuh"
 #include "mt_device.cuh"
 #include "mt_jump.hpp"
 #include "oprobit.cuh"
@@ -552,17 +553,11 @@ template <typename Real> struct Trainer : TrainerBase {
                    std::chrono::duration<double, std::milli>(now - t_last).count());
       t_last = now;
     };
-    HostCs<Real> Xh = host_from_api<Real>(X_api, "X");
-    tick("copy + validate CSR");
-    if (Xh.n_major != n_y) { // BaseFMTrainer.hpp:69-76
+    if (X_api.n_rows != n_y) { // BaseFMTrainer.hpp:69-76
       std::ostringstream ss;
-      ss << "Shape mismatch: X has size " << Xh.n_major << " and y has size " << n_y;
+      ss << "Shape mismatch: X has size " << X_api.n_rows << " and y has size " << n_y;
       throw std::runtime_error(ss.str());
     }
-    if (has_duplicate_entries(Xh))
-      throw std::invalid_argument(
-          "X lists the same (row, column) twice; sum duplicates first (X.sum_duplicates()).");
-    tick("duplicate check");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device)
       throw CudaError("no usable CUDA device: the myfm_b200 engine has no CPU fallback.");
@@ -576,9 +571,20 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : z_free)
       MYFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    data.launch_counter = &launches;
 
-    // dependency levels, device row order, sweep work items (host_data.hpp)
-    {
+    // Field-shaped main tables are prepared on the device (prep_device.cuh); everything else — and
+    // any input that path declines — on the host (host_data.hpp), which also owns the error messages.
+    HostCs<Real> Xh;
+    const bool device_prepared = prepare_on_device(X_api, n_rel, o, tick);
+    if (!device_prepared) {
+      Xh = host_from_api<Real>(X_api, "X");
+      tick("copy + validate CSR");
+      if (has_duplicate_entries(Xh))
+        throw std::invalid_argument(
+            "X lists the same (row, column) twice; sum duplicates first (X.sum_duplicates()).");
+      tick("duplicate check");
+      // dependency levels, device row order, sweep work items (host_data.hpp)
       HostCs<Real> Xth0 = host_transpose(Xh);
       tick("transpose");
       int n_levels = 0, primary = -1;
@@ -618,13 +624,14 @@ template <typename Real> struct Trainer : TrainerBase {
       plan.primary_level = primary;
       tick("sweep plan");
       Xt.upload(Xth, stream);
-      setup_field_path(Xh, Xth, level, n_levels, n_rel);
+      setup_field_path(&Xh, Xth, level, n_levels, n_rel);
       MYFM_CUDA(cudaStreamSynchronize(stream));
       tick("CSC upload + field path");
       setup_tile_path(Xh);
       tick("tile path");
     }
-    perm_dev.upload(perm, stream);
+    if (!device_prepared)
+      perm_dev.upload(perm, stream);
     { // key of every device row's latent stream (PHILOX): its global row index
       if (o.row_ids && o.n_row_ids != static_cast<int64_t>(perm.size()))
         throw std::invalid_argument("row_ids must have one entry per training row of this shard.");
@@ -643,8 +650,8 @@ template <typename Real> struct Trainer : TrainerBase {
     seg_partial.alloc(2 * static_cast<size_t>(std::max(1, plan.max_seg_items)));
     seg_theta_old.alloc(std::max(1, plan.max_seg_items));
 
-    data.launch_counter = &launches;
-    data.build(Xh, n_rel, relations, stream, &perm);
+    if (!device_prepared)
+      data.build(Xh, n_rel, relations, stream, &perm);
     tick("CSR upload");
     N = data.n_rows, D = data.dim_main, D_all = data.dim_all;
     if (static_cast<int64_t>(cfg.group_index.size()) != D_all)
@@ -1182,20 +1189,160 @@ template <typename Real> struct Trainer : TrainerBase {
   // ---- field path (field_sweep.cuh) ---------------------------------------------------------------
   // Decides whether the main table is a stack of position-aligned fields and, if so, builds the
   // extra arrays of that path.  Xh: CSR in device row order, Xth its transpose.
-  void setup_field_path(const HostCs<Real> &Xh, const HostCs<Real> &Xth, const std::vector<int> &level,
-                        int n_levels, int n_rel) {
+  // Field-shaped main tables: row order, permuted CSR, CSC and the field arrays are built on the
+  // device (prep_device.cuh); the host checks the row pointers, plans the work items from the
+  // column pointers and keeps the permutation.  Returns false (nothing changed) when the input is
+  // not of that shape — the host path then prepares it, or reports what is wrong with it.
+  template <typename Tick>
+  bool prepare_on_device(const myfm_csr_t &X, int n_rel, const myfm_engine_options_t &o, Tick &tick) {
+    const char *off = std::getenv("MYFM_HOST_SETUP"), *tile = std::getenv("MYFM_TILE_PATH");
+    if ((off && off[0] == '1') || (tile && tile[0] == '1') || n_rel > 0)
+      return false;
+    const int64_t n = X.n_rows, n_cols = X.n_cols;
+    if (n < 1024 || n_cols <= 0 || n_cols >= std::numeric_limits<int>::max() || !X.indptr || !X.indices || !X.data)
+      return false;
+    const int64_t nnz = X.indptr[n];
+    if (X.indptr[0] != 0 || nnz <= 0 || nnz >= std::numeric_limits<int>::max() || nnz % n)
+      return false;
+    const int L = static_cast<int>(nnz / n);
+    if (L < 2 || L > PREP_MAX_FIELDS)
+      return false;
+    if (o.column_level && o.n_column_level != n_cols)
+      return false;
+    // every row holds exactly L entries; are all values 1?
+    std::atomic<bool> regular{true}, unit{true};
+    parallel_parts(parts_for(nnz), [&](int t, int n_parts) {
+      auto [r0, r1] = part_range(n, t, n_parts);
+      for (int64_t i = r0; i < r1; i++)
+        if (X.indptr[i + 1] != (i + 1) * L) {
+          regular = false;
+          return;
+        }
+      auto [p0, p1] = part_range(nnz, t, n_parts);
+      bool ones = true;
+      for (int64_t p = p0; p < p1 && ones; p++)
+        ones = X.data[p] == 1.0;
+      if (!ones)
+        unit = false;
+    });
+    if (!regular)
+      return false;
+    tick("row pointers / unit values (host)");
+    DevBuf<int> idx_in(nnz), given_level;
+    DevBuf<double> val_in;
+    idx_in.upload(X.indices, nnz, stream);
+    if (!unit)
+      val_in.upload(X.data, nnz, stream);
+    if (o.column_level)
+      given_level.upload(o.column_level, n_cols, stream);
+    std::vector<int> stat(129, 0);
+    for (int k = 0; k < 64; k++)
+      stat[k] = std::numeric_limits<int>::max(), stat[64 + k] = -1;
+    DevBuf<int> stat_dev;
+    stat_dev.upload(stat, stream);
+    k_prep_scan<<<592, 256, 0, stream>>>(n, L, static_cast<int>(n_cols), idx_in.p, given_level.p, stat_dev.p);
+    launched();
+    stat_dev.download(stat.data(), stat.size(), stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    tick("upload + field scan");
+    if (stat[128])
+      return false;
+    for (int k = 0; k + 1 < L; k++)
+      if (stat[64 + k] >= stat[k + 1])
+        return false; // the fields' column ranges must ascend with the position
+    // rows by their first-field column
+    int bits = 1;
+    while ((int64_t(1) << bits) < n_cols)
+      bits++;
+    PrepSorter sorter;
+    DevBuf<int> keys(n), keys_sorted(n), rows(n);
+    perm_dev.alloc(n);
+    const int grid_n = ceil_div(n, 256);
+    k_prep_keys<<<grid_n, 256, 0, stream>>>(n, L, 0, idx_in.p, keys.p, rows.p);
+    sorter.sort(keys.p, keys_sorted.p, rows.p, perm_dev.p, n, bits, stream);
+    // permuted CSR, field arrays, column counts
+    data.stream = stream;
+    data.n_rows = n, data.dim_main = n_cols, data.dim_all = n_cols;
+    data.X.n_major = n, data.X.n_minor = n_cols, data.X.nnz = nnz;
+    data.X.ptr.alloc(n + 1), data.X.idx.alloc(nnz), data.X.val.alloc(nnz);
+    data.row_len = L, data.unit = unit;
+    main_unit = unit, main_row_len = L;
+    f_tail_idx.alloc(static_cast<size_t>(L - 1) * n);
+    if (!unit)
+      f_tail_val.alloc(static_cast<size_t>(L - 1) * n), f_own_val.alloc(n);
+    DevBuf<int> col_count(n_cols + 1);
+    col_count.zero(stream);
+    k_prep_permute<Real><<<ceil_div(n + 1, 256), 256, 0, stream>>>(
+        n, L, perm_dev.p, idx_in.p, unit ? nullptr : val_in.p, data.X.ptr.p, data.X.idx.p, data.X.val.p, f_tail_idx.p,
+        unit ? nullptr : f_tail_val.p, unit ? nullptr : f_own_val.p, col_count.p);
+    // CSC: column pointers, then the entries field by field
+    Xt.n_major = n_cols, Xt.n_minor = n, Xt.nnz = nnz;
+    Xt.ptr.alloc(n_cols + 1), Xt.idx.alloc(nnz), Xt.val.alloc(nnz);
+    sorter.exclusive_sum(col_count.p, Xt.ptr.p, n_cols + 1, stream);
+    k_prep_csc_first<Real><<<grid_n, 256, 0, stream>>>(n, unit ? nullptr : f_own_val.p, Xt.idx.p, Xt.val.p);
+    launched(4);
+    for (int k = 1; k < L; k++) {
+      const int *field_cols = f_tail_idx.p + static_cast<size_t>(k - 1) * n;
+      k_prep_keys<<<grid_n, 256, 0, stream>>>(n, 1, 0, field_cols, keys.p, rows.p);
+      sorter.sort(keys.p, keys_sorted.p, rows.p, Xt.idx.p + static_cast<size_t>(k) * n, n, bits, stream);
+      k_prep_csc_val<Real><<<grid_n, 256, 0, stream>>>(
+          n, Xt.idx.p + static_cast<size_t>(k) * n, unit ? nullptr : f_tail_val.p + static_cast<size_t>(k - 1) * n,
+          Xt.val.p + static_cast<size_t>(k) * n);
+      launched(3);
+    }
+    MYFM_CUDA(cudaGetLastError());
+    // to the host: the permutation and the column pointers
+    perm.resize(n);
+    HostCs<Real> Xth; // column pointers only
+    Xth.n_major = n_cols, Xth.n_minor = n;
+    Xth.ptr.resize(n_cols + 1);
+    perm_dev.download(perm.data(), n, stream);
+    Xt.ptr.download(Xth.ptr.data(), n_cols + 1, stream);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    tick("device: sorts, CSR, CSC");
+    std::vector<int> level;
+    const int n_levels = L;
+    if (o.column_level) {
+      level.assign(o.column_level, o.column_level + n_cols);
+      for (int lv : level)
+        if (lv < 0 || lv >= L)
+          return false; // (the host path reports what is wrong)
+    } else {
+      level.assign(n_cols, 0); // columns without rows conflict with nothing: level 0, as compute_levels has it
+      for (int k = 1; k < L; k++)
+        for (int j = stat[k]; j <= stat[64 + k]; j++)
+          if (Xth.ptr[j + 1] > Xth.ptr[j])
+            level[j] = k;
+    }
+    LevelFlags flags;
+    flags.unit.assign(L, unit ? 1 : 0), flags.contig.assign(L, 0);
+    flags.contig[0] = 1;
+    plan = make_sweep_plan(Xth, level, n_levels, SWEEP_WARP_MAX, SWEEP_CHUNK, -1, &flags);
+    plan.primary_level = 0;
+    setup_field_path(nullptr, Xth, level, n_levels, 0, &flags);
+    MYFM_CUDA(cudaStreamSynchronize(stream));
+    tick("work items + field path");
+    return true;
+  }
+
+  // Xh: CSR in device row order, or nullptr when the table was prepared on the device (then the
+  // field structure is established, the field arrays exist already, Xth carries column pointers
+  // only and a first-field column's rows are [ptr[j], ptr[j + 1]) themselves).
+  void setup_field_path(const HostCs<Real> *Xh, const HostCs<Real> &Xth, const std::vector<int> &level,
+                        int n_levels, int n_rel, const LevelFlags *known = nullptr) {
     field_path = false;
     const char *off = std::getenv("MYFM_NO_FIELD_PATH");
     if (off && off[0] == '1')
       return;
     const int L = main_row_len;
-    const int64_t n = Xh.n_major;
+    const int64_t n = Xth.n_minor;
     if (n_rel > 0 || n == 0 || L < 2 || L != n_levels || plan.primary_level != 0 || !plan.levels[0].contig)
       return;
-    for (int64_t i = 0; i < n; i++)
-      for (int k = 0; k < L; k++)
-        if (level[Xh.idx[i * L + k]] != k)
-          return;
+    if (Xh)
+      for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < L; k++)
+          if (level[Xh->idx[i * L + k]] != k)
+            return;
     int lo = std::numeric_limits<int>::max(), hi = -1, longest0 = 0;
     for (int64_t j = 0; j < Xth.n_major; j++) {
       if (level[j] == L - 1)
@@ -1213,15 +1360,15 @@ template <typename Real> struct Trainer : TrainerBase {
       return;
     f_last_base = lo, f_tab = static_cast<int>(tab), f_tail = L - 1;
 
-    SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_CTA_MAX, FIELD_CTA_MAX, 0); // longest first
-    SweepPlan pL = make_sweep_plan(Xth, level, n_levels, STATS_WARP_MAX, STATS_CHUNK, L - 1);
+    SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_CTA_MAX, FIELD_CTA_MAX, 0, known); // longest first
+    SweepPlan pL = make_sweep_plan(Xth, level, n_levels, STATS_WARP_MAX, STATS_CHUNK, L - 1, known);
     f_level0 = p0.levels[0], f_levelL = pL.levels[L - 1];
     // level-0 items carry row ranges: a contiguous column's rows are idx[lo] .. idx[lo] + len
     const int rows_per_warp = 32 * (sizeof(Real) == 8 ? 4 : 8);
     f_nCC = f_nCR = f_nG = f_nW = 0;
     for (SweepItem &it : p0.items) {
       const int len = it.hi - it.lo;
-      const int first_row = len ? Xth.idx[it.lo] : 0;
+      const int first_row = len ? (Xh ? Xth.idx[it.lo] : it.lo) : 0;
       it.lo = first_row, it.hi = first_row + len;
       if (len > rows_per_warp * FIELD_WARPS)
         f_nCC++;
@@ -1261,20 +1408,24 @@ template <typename Real> struct Trainer : TrainerBase {
     f_partial.alloc(2 * static_cast<size_t>(std::max(1, f_levelL.c0 - f_levelL.s0)));
     f_chunk_done.alloc(std::max(1, f_levelL.c0 - f_levelL.s0));
     f_chunk_done.zero(stream);
-    std::vector<int> tail(static_cast<size_t>(f_tail) * n);
-    for (int64_t i = 0; i < n; i++)
-      for (int k = 1; k < L; k++)
-        tail[static_cast<size_t>(k - 1) * n + i] = Xh.idx[i * L + k];
-    f_tail_idx.upload(tail, stream);
-    if (!main_unit) {
-      std::vector<Real> tv(static_cast<size_t>(f_tail) * n), ov(n);
-      for (int64_t i = 0; i < n; i++) {
-        ov[i] = Xh.val[i * L];
+    std::vector<int> tail;
+    std::vector<Real> tv, ov;
+    if (Xh) {
+      tail.resize(static_cast<size_t>(f_tail) * n);
+      for (int64_t i = 0; i < n; i++)
         for (int k = 1; k < L; k++)
-          tv[static_cast<size_t>(k - 1) * n + i] = Xh.val[i * L + k];
+          tail[static_cast<size_t>(k - 1) * n + i] = Xh->idx[i * L + k];
+      f_tail_idx.upload(tail, stream);
+      if (!main_unit) {
+        tv.resize(static_cast<size_t>(f_tail) * n), ov.resize(n);
+        for (int64_t i = 0; i < n; i++) {
+          ov[i] = Xh->val[i * L];
+          for (int k = 1; k < L; k++)
+            tv[static_cast<size_t>(k - 1) * n + i] = Xh->val[i * L + k];
+        }
+        f_tail_val.upload(tv, stream);
+        f_own_val.upload(ov, stream);
       }
-      f_tail_val.upload(tv, stream);
-      f_own_val.upload(ov, stream);
     }
     if (world > 1) { // column slots and the statistics buffer of the two-pass schedule
       f_item_slot0.upload(p0.item_slot, stream);

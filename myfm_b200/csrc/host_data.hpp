@@ -420,9 +420,15 @@ HostCs<Real> permute_rows(const HostCs<Real> &csr, const std::vector<int> &perm)
   return out;
 }
 
+// What make_sweep_plan finds out per level by looking at every entry, when the caller knows it already
+// (device-side preparation, csrc/prep_device.cuh: the CSC entries never come to the host).
+struct LevelFlags {
+  std::vector<char> unit, contig;
+};
+
 template <typename Real>
 SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level, int n_levels,
-                          int warp_max, int chunk, int only_level = -1) {
+                          int warp_max, int chunk, int only_level = -1, const LevelFlags *known = nullptr) {
   SweepPlan plan;
   plan.levels.resize(n_levels);
   std::vector<std::vector<int>> cols(n_levels);
@@ -440,6 +446,8 @@ SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level
     std::stable_sort(c.begin(), c.end(), [&](int x, int y) { return len(x) > len(y); });
     for (int j : c) {
       L.nnz += len(j);
+      if (known)
+        continue;
       for (int p = csc.ptr[j]; p < csc.ptr[j + 1]; p++) {
         if (csc.val[p] != Real(1))
           L.unit = false;
@@ -447,6 +455,8 @@ SweepPlan make_sweep_plan(const HostCs<Real> &csc, const std::vector<int> &level
           L.contig = false;
       }
     }
+    if (known)
+      L.unit = known->unit[l] != 0, L.contig = known->contig[l] != 0;
     L.s0 = static_cast<int>(plan.items.size());
     std::vector<int> by_index(c);
     std::sort(by_index.begin(), by_index.end());
