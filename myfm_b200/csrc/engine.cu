@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <thread>
 
@@ -850,7 +851,7 @@ template <typename Real> struct Trainer : TrainerBase {
       const char *no_graph = std::getenv("MYFM_NO_GRAPH");
       use_graphs = !(no_graph && no_graph[0] == '1');
     }
-    if (field_path)
+    if (field_path || tile_path)
       f_sched.alloc(2 * (static_cast<size_t>(K) + 2));
     setup_rng();
     const bool ordered = cfg.task_type == MYFM_TASK_ORDERED;
@@ -1250,6 +1251,13 @@ template <typename Real> struct Trainer : TrainerBase {
     for (int k = 0; k + 1 < L; k++)
       if (stat[64 + k] >= stat[k + 1])
         return false; // the fields' column ranges must ascend with the position
+    {
+      int dev_smem = 0;
+      MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+      const int64_t tab = static_cast<int64_t>(stat[64 + L - 1]) - stat[L - 1] + 1;
+      if (tab * FieldTab<Real>::BYTES_PER_COLUMN > dev_smem - 4096 && L == 2 && world == 1)
+        return false; // two fields, table too large for the field path: the tile path (host-built B order) takes it
+    }
     // rows by their first-field column
     int bits = 1;
     while ((int64_t(1) << bits) < n_cols)
@@ -1267,7 +1275,7 @@ template <typename Real> struct Trainer : TrainerBase {
     data.X.ptr.alloc(n + 1), data.X.idx.alloc(nnz), data.X.val.alloc(nnz);
     data.row_len = L, data.unit = unit;
     main_unit = unit, main_row_len = L;
-    f_tail_idx.alloc(static_cast<size_t>(L - 1) * n);
+    f_tail_idx.alloc(static_cast<size_t>(L - 1) * n + 4); // (+4: bulk copies of the last field's indices end on 16 bytes)
     if (!unit)
       f_tail_val.alloc(static_cast<size_t>(L - 1) * n), f_own_val.alloc(n);
     DevBuf<int> col_count(n_cols + 1);
@@ -1330,7 +1338,7 @@ template <typename Real> struct Trainer : TrainerBase {
   // only and a first-field column's rows are [ptr[j], ptr[j + 1]) themselves).
   void setup_field_path(const HostCs<Real> *Xh, const HostCs<Real> &Xth, const std::vector<int> &level,
                         int n_levels, int n_rel, const LevelFlags *known = nullptr) {
-    field_path = false;
+    field_path = false, f_structure = false;
     const char *off = std::getenv("MYFM_NO_FIELD_PATH");
     if (off && off[0] == '1')
       return;
@@ -1356,9 +1364,22 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     MYFM_CUDA(cudaDeviceGetAttribute(&f_sm_count, cudaDevAttrMultiProcessorCount, device));
     const int64_t tab = static_cast<int64_t>(hi) - lo + 1;
-    if (tab * FieldTab<Real>::BYTES_PER_COLUMN > dev_smem - 4096)
-      return;
+    // the field STRUCTURE is established here; the field path's kernels also need the last field's
+    // {theta_old, theta_new, theta_next} table in shared memory (the tile path only theta_next)
+    const bool table_fits = tab * FieldTab<Real>::BYTES_PER_COLUMN <= dev_smem - 4096;
     f_last_base = lo, f_tab = static_cast<int>(tab), f_tail = L - 1;
+    {
+      // Opt-in (MYFM_STAGING=1): measured equal to the direct-load kernel on ml10m (1.90 vs 1.88 ms per sweep
+      // for the streaming level: one column of prefetch does not cover the DRAM latency, and there is no room
+      // for deeper buffers next to the table), and the larger shared-memory carve-out slows the kernels
+      // that follow, so it is not the default.
+      const char *staging = std::getenv("MYFM_STAGING");
+      f_staged_smem = (static_cast<size_t>(tab) * FieldTab<Real, true>::BYTES_PER_COLUMN + 15) / 16 * 16 +
+                      static_cast<size_t>(FIELD_WARPS) * FieldStageSize<Real>::BYTES;
+      // (the last field's index array must start on a 16-byte boundary: it follows L - 2 arrays of n ints)
+      f_staged = sizeof(Real) == 4 && f_staged_smem + 2048 <= static_cast<size_t>(dev_smem) &&
+                 (static_cast<int64_t>(L - 2) * n) % 4 == 0 && staging && staging[0] == '1';
+    }
 
     SweepPlan p0 = make_sweep_plan(Xth, level, n_levels, FIELD_CTA_MAX, FIELD_CTA_MAX, 0, known); // longest first
     SweepPlan pL = make_sweep_plan(Xth, level, n_levels, STATS_WARP_MAX, STATS_CHUNK, L - 1, known);
@@ -1415,6 +1436,7 @@ template <typename Real> struct Trainer : TrainerBase {
       for (int64_t i = 0; i < n; i++)
         for (int k = 1; k < L; k++)
           tail[static_cast<size_t>(k - 1) * n + i] = Xh->idx[i * L + k];
+      tail.resize(tail.size() + 4, 0); // bulk copies of the last field's indices end on 16-byte boundaries
       f_tail_idx.upload(tail, stream);
       if (!main_unit) {
         tv.resize(static_cast<size_t>(f_tail) * n), ov.resize(n);
@@ -1447,8 +1469,10 @@ template <typename Real> struct Trainer : TrainerBase {
     f_pend_told.zero(stream);
     f_pend_tnew.zero(stream);
     MYFM_CUDA(cudaStreamSynchronize(stream)); // host staging vectors die here
-    field_path = true;
+    f_structure = true;
+    field_path = table_fits;
   }
+  bool f_structure = false; // the main table is a stack of position-aligned fields (field / tile path arrays exist)
 
   // Collective: decides whether every level-0 column lives on one rank only and, if so, restricts
   // this rank's level-0 work items to the columns it owns (columns without rows anywhere are dealt
@@ -1661,10 +1685,14 @@ template <typename Real> struct Trainer : TrainerBase {
   // items and the sliced-ELL "B order" of the last field.  Xh: CSR in device row order.
   void setup_tile_path(const HostCs<Real> &Xh) {
     tile_path = false;
-    // Opt-in (MYFM_TILE_PATH=1): parity-green, but measured at 112 us per vector against the field
-    // path's 107 us on the ml10m workload (DESIGN.md section 3c has the profile), so not the default.
-    const char *on = std::getenv("MYFM_TILE_PATH");
-    if (!(on && on[0] == '1') || !field_path || f_tail != 1 || world > 1)
+    // Opt-in (MYFM_TILE_PATH=1) where the field path applies: parity-green, but measured at 112 us per vector
+    // against the field path's 107 us on the ml10m workload (DESIGN.md section 3c has the profile).
+    // It also takes over, unasked, when the field path's table does not fit the shared memory but the tile
+    // path's does (f64 with ~10^4 last-field columns: ml10m in double), where the alternative is the general
+    // read-modify-write level kernels.
+    const char *on = std::getenv("MYFM_TILE_PATH"), *never = std::getenv("MYFM_NO_TILE_PATH");
+    const bool asked = on && on[0] == '1';
+    if ((never && never[0] == '1') || !f_structure || (!asked && field_path) || f_tail != 1 || world > 1)
       return;
     const int64_t n = Xh.n_major;
     int dev_smem = 0;
@@ -1971,17 +1999,27 @@ template <typename Real> struct Trainer : TrainerBase {
   }
   template <bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE>
   void launch_field_stream_as(const FieldStreamArgs<Real> &a) {
-    auto kernel = k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND, MODE>;
-    const size_t smem = static_cast<size_t>(f_tab) * FieldTab<Real>::BYTES_PER_COLUMN;
-    static size_t configured = 0; // per instantiation
-    if (smem > configured) {
-      MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-      configured = smem;
+    // UNIT tables, fused pass: the warp class stages its rows through TMA bulk copies when the compact table
+    // and the 32 staging buffers fit the shared memory (opt-in: MYFM_STAGING=1)
+    if (UNIT && MODE == FIELD_FUSED && f_staged) {
+      launch_field_stream_kernel(k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND, MODE, true>, a, f_staged_smem);
+      return;
+    }
+    launch_field_stream_kernel(k_field_stream<Real, IS_V, UNIT, HAS_MID, PEND, MODE, false>, a,
+                               static_cast<size_t>(f_tab) * FieldTab<Real>::BYTES_PER_COLUMN);
+  }
+  template <typename Kernel> void launch_field_stream_kernel(Kernel kernel, const FieldStreamArgs<Real> &a, size_t smem) {
+    static std::map<const void *, size_t> configured; // dynamic shared memory granted per kernel
+    size_t &have = configured[reinterpret_cast<const void *>(kernel)];
+    if (smem > have) {
+      MYFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      have = smem;
     }
     kernel<<<f_sm_count, FIELD_THREADS, smem, stream>>>(a);
     launched();
   }
+  bool f_staged = false;
+  size_t f_staged_smem = 0;
 
   // One vector (w or a factor column) over the main table: streaming pass, middle levels, gather.
   template <bool IS_V>
@@ -2454,7 +2492,7 @@ template <typename Real> struct Trainer : TrainerBase {
   void sweep_body(const Real *z) {
     HyperView<Real> h = hv();
     const SweepLayout &L = layout;
-    if (field_path) { // work counters of this sweep's streaming passes; nothing is pending after update_e
+    if (field_path || tile_path) { // work counters of this sweep's streaming passes; nothing is pending after update_e
       f_sched.zero(stream);
       f_launch = 0, f_pending_valid = false;
     }
@@ -2662,7 +2700,7 @@ template <typename Real> struct Trainer : TrainerBase {
       out[i] = h[i];
   }
   void get_q(double *out) override {
-    if (field_path && K > 0) // the field path leaves q undefined between sweeps: q = X V[:, K-1]
+    if ((field_path || tile_path) && K > 0) // the field / tile path leave q undefined between sweeps: q = X V[:, K-1]
       spmv(data.X, V.p + static_cast<size_t>(D_all) * (K - 1), q_ptr(), false, 2);
     std::vector<Real> h(N);
     export_component(1, h.data());

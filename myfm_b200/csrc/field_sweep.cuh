@@ -36,6 +36,50 @@ constexpr int STATS_CHUNK = 8192;     // one CTA per column up to here, chunks o
 
 enum { PEND_NONE = 0, PEND_W = 1, PEND_V = 2 };
 
+// ---- TMA (1-D bulk copy) and mbarrier primitives ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}" ::"r"(smem_addr(bar)),
+               "r"(parity)
+               : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// writes made through the generic proxy (ordinary st.shared) become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
+
 
 // ------------------------------------------------------------------------------------------------
 // Row shards on one NVLink / NVSwitch node: the all-reduce of the column statistics is fused into
@@ -173,8 +217,9 @@ enum { FIELD_FUSED = 0, FIELD_STATS = 1, FIELD_UPDATE = 2 };
 // Shared-memory table of the last level's columns: {theta_old, theta_new} of the update left
 // pending and theta of the vector being swept.  f32: one 16-byte record per column (one LDS.128 per
 // row instead of three scattered LDS.32); f64: three arrays.
-template <typename Real> struct FieldTab;
-template <> struct FieldTab<float> {
+// COMPACT (f32 with staged rows, below): 12 bytes per column — {theta_old, theta_new} pairs, then theta_next.
+template <typename Real, bool COMPACT = false> struct FieldTab;
+template <> struct FieldTab<float, false> {
   static constexpr int BYTES_PER_COLUMN = 16;
   static __device__ __forceinline__ void get(const float *base, int, int j, float &told, float &tnew, float &tnext) {
     const float4 r = reinterpret_cast<const float4 *>(base)[j];
@@ -184,7 +229,18 @@ template <> struct FieldTab<float> {
     reinterpret_cast<float4 *>(base)[j] = make_float4(told, tnew, tnext, 0.f);
   }
 };
-template <> struct FieldTab<double> {
+template <> struct FieldTab<float, true> {
+  static constexpr int BYTES_PER_COLUMN = 12;
+  static __device__ __forceinline__ void get(const float *base, int n, int j, float &told, float &tnew, float &tnext) {
+    const float2 r = reinterpret_cast<const float2 *>(base)[j];
+    told = r.x, tnew = r.y, tnext = base[2 * n + j];
+  }
+  static __device__ __forceinline__ void put(float *base, int n, int j, float told, float tnew, float tnext) {
+    reinterpret_cast<float2 *>(base)[j] = make_float2(told, tnew);
+    base[2 * n + j] = tnext;
+  }
+};
+template <bool COMPACT> struct FieldTab<double, COMPACT> {
   static constexpr int BYTES_PER_COLUMN = 24;
   static __device__ __forceinline__ void get(const double *base, int n, int j, double &told, double &tnew,
                                              double &tnext) {
@@ -195,15 +251,37 @@ template <> struct FieldTab<double> {
   }
 };
 
+// Rows of a warp's column staged in shared memory by TMA bulk copies (k_field_stream<..., STAGED>):
+// eq[i - eq_row0], idx[i - idx_row0] for the rows i of the column (the copies start on 16-byte
+// boundaries, so they begin up to one / three rows early).
+template <typename Real> struct FieldStage {
+  const Pair<Real> *eq = nullptr;
+  const int *idx = nullptr;
+  int eq_row0 = 0, idx_row0 = 0;
+};
+constexpr int FIELD_STAGE_ROWS = 256; // the warp class: up to 32 lanes x 8 rows (f32)
+constexpr int FIELD_STAGE_IDX_BYTES = (FIELD_STAGE_ROWS + 8) * 4;
+template <typename Real> struct FieldStageSize {
+  static constexpr int EQ_BYTES = (FIELD_STAGE_ROWS + 2) * static_cast<int>(sizeof(Pair<Real>));
+  static constexpr int BYTES = EQ_BYTES + FIELD_STAGE_IDX_BYTES;
+};
+
 // U rows of the streaming pass in flight per thread: all global loads are issued first (load),
 // the shared-memory lookups and the arithmetic follow (finish) — a row's table index comes out of
 // its own load, so interleaving the two would serialise the rows on the memory latency.
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U> struct FieldBatch {
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U, bool COMPACT = false> struct FieldBatch {
   static constexpr bool NEED_LAST = IS_V || PEND != PEND_NONE;
   Pair<Real> v[U];
   int jl[U];
   Real xl[U], x0[U];
 
+  // the same from the warp's staged copy of its column (UNIT tables only)
+  __device__ __forceinline__ void load(const FieldStreamArgs<Real> &a, const FieldStage<Real> &st, int u, int i) {
+    v[u] = st.eq[i - st.eq_row0];
+    jl[u] = 0, xl[u] = Real(1), x0[u] = Real(1);
+    if (NEED_LAST)
+      jl[u] = st.idx[i - st.idx_row0] - a.last_base;
+  }
   __device__ __forceinline__ void load(const FieldStreamArgs<Real> &a, int u, int i) {
     v[u] = __ldcg(a.eq + i);
     jl[u] = 0, xl[u] = Real(1), x0[u] = Real(1);
@@ -224,7 +302,7 @@ template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int U> st
     const Real xlu = xl[u];
     Real told = 0, tnew = 0, tnext = 0;
     if (NEED_LAST)
-      FieldTab<Real>::get(s_tab, a.n_tab, jl[u], told, tnew, tnext);
+      FieldTab<Real, COMPACT>::get(s_tab, a.n_tab, jl[u], told, tnew, tnext);
     if (PEND == PEND_V) { // FMTrainer.hpp:366-374 of the previous factor's last-level column
       const Real h = xlu * (q - xlu * told);
       e = e + h * (tnew - told);
@@ -278,12 +356,12 @@ __device__ __forceinline__ Pair<Real> field_update(Real e, Real q, Real x0, Real
 
 // One pass of NT cooperating threads (t = 0 .. NT-1) over the rows [lo, hi) of a column, U rows
 // per thread in flight.  UPDATE = false: accumulates the statistics; true: writes e and q back.
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int NT, bool UPDATE>
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int NT, bool UPDATE, bool COMPACT = false>
 __device__ __forceinline__ void field_pass(const FieldStreamArgs<Real> &a, const Real *s_tab, int lo, int hi, int t,
                                            Real theta_old, Real theta_new, Real alpha, Real &sq, Real &lin) {
   constexpr int U = 4;
   for (int base = lo + t; base < hi; base += U * NT) {
-    FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, U> b;
+    FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, U, COMPACT> b;
 #pragma unroll
     for (int u = 0; u < U; u++)
       b.load(a, u, min(base + u * NT, hi - 1));
@@ -334,20 +412,31 @@ __device__ __forceinline__ void field_group_sum(Real &sq, Real &lin, Real *s_par
 // in registers between the reduction and the update, so every row is read once and written once.
 // FULL: slots 0 .. NS-2 hold a row in every thread (the caller picked NS = ceil(rows / threads)),
 // only the last slot is ragged; otherwise every slot is checked.
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW, int NS, bool FULL>
+// STAGED: the rows come from the warp's shared-memory copy `st`; `after_rows()` runs once they sit in
+// registers (the warp then starts the copy of its next column).
+struct FieldNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW, int NS, bool FULL,
+          bool COMPACT = false, bool STAGED = false, typename Hook = FieldNoHook>
 __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a, const Real *s_tab, int4 it, int t,
                                                   Real theta_old, Real alpha, Real lam, Real mu, Real z,
                                                   Real *s_part, int parity, int grp, int wig, int lane,
-                                                  Real theta_given, Real &sq, Real &lin) {
+                                                  Real theta_given, Real &sq, Real &lin,
+                                                  const FieldStage<Real> &st = FieldStage<Real>(),
+                                                  Hook after_rows = Hook()) {
   constexpr int NT = 32 * GW;
-  FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, NS> b;
+  FieldBatch<Real, IS_V, UNIT, HAS_MID, PEND, NS, COMPACT> b;
   Real e[NS], q[NS], x0[NS];
   const int i0 = it.y + t;
   bool ok[NS];
 #pragma unroll
   for (int s = 0; s < NS; s++) {
     ok[s] = (FULL && s < NS - 1) || i0 + NT * s < it.z;
-    b.load(a, s, ok[s] ? i0 + NT * s : it.z - 1);
+    if (STAGED)
+      b.load(a, st, s, ok[s] ? i0 + NT * s : it.z - 1);
+    else
+      b.load(a, s, ok[s] ? i0 + NT * s : it.z - 1);
   }
   sq = 0, lin = 0;
 #pragma unroll
@@ -356,6 +445,7 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
     if (MODE != FIELD_UPDATE && ok[s])
       field_stats<Real, IS_V>(e[s], q[s], x0[s], theta_old, alpha, sq, lin);
   }
+  after_rows();
   if (MODE != FIELD_UPDATE)
     field_group_sum<Real, GW>(sq, lin, s_part, parity, grp, wig, lane);
   if (MODE == FIELD_STATS)
@@ -370,18 +460,21 @@ __device__ __forceinline__ Real field_column_regs(const FieldStreamArgs<Real> &a
 }
 
 // Picks the instantiation for the column's slot count (warp-uniform switch).
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW>
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, int GW, bool COMPACT = false,
+          bool STAGED = false, typename Hook = FieldNoHook>
 __device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real> &a, const Real *s_tab, int4 it, int t,
                                                       Real theta_old, Real alpha, Real lam, Real mu, Real z,
                                                       Real *s_part, int parity, int grp, int wig, int lane,
-                                                      Real theta_given, Real &sq, Real &lin) {
+                                                      Real theta_given, Real &sq, Real &lin,
+                                                      const FieldStage<Real> &st = FieldStage<Real>(),
+                                                      Hook after_rows = Hook()) {
   constexpr int R = sizeof(Real) == 8 ? 4 : 8, NT = 32 * GW;
   const int n_slots = (it.z - it.y + NT - 1) / NT;
 #define MYFM_SLOTS(NS)                                                                             \
   case NS:                                                                                         \
-    return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, GW, (NS <= R ? NS : R), true>(                 \
-        a, s_tab, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane,           \
-        theta_given, sq, lin);
+    return field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, GW, (NS <= R ? NS : R), true, COMPACT, STAGED,  \
+                             Hook>(a, s_tab, it, t, theta_old, alpha, lam, mu, z, s_part, parity, grp, wig, lane,  \
+                                   theta_given, sq, lin, st, after_rows);
   switch (n_slots) {
     MYFM_SLOTS(1)
     MYFM_SLOTS(2)
@@ -394,6 +487,7 @@ __device__ __forceinline__ Real field_column_dispatch(const FieldStreamArgs<Real
   }
 #undef MYFM_SLOTS
   // no local rows (an empty column, or a column whose rows live on other ranks)
+  after_rows();
   sq = 0, lin = 0;
   if (MODE == FIELD_STATS)
     return theta_old;
@@ -419,15 +513,25 @@ __device__ __forceinline__ void field_finish_column(const FieldStreamArgs<Real> 
 //   nCR  up to 32 R FIELD_WARPS rows:       the whole CTA, rows in registers
 //   nG   up to 32 R FIELD_GROUP_WARPS rows: a group of four warps, rows in registers
 //   nW   up to 32 R rows:                   one warp, rows in registers, handed out dynamically
-template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE>
+// STAGED (UNIT tables, FIELD_FUSED): the warp class reads its rows from a per-warp shared-memory
+// buffer that a TMA bulk copy (cp.async.bulk, mbarrier-signalled) filled while the warp was busy
+// with the previous column — the copy of column c + 1 is issued as soon as column c's rows sit in
+// registers, so its latency hides behind c's reduction, draw and write-back.  The table then uses
+// the 12-byte layout to leave room for the 32 buffers.
+template <typename Real, bool IS_V, bool UNIT, bool HAS_MID, int PEND, int MODE, bool STAGED = false>
 __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_constant__ FieldStreamArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ Real scratch[32];
   __shared__ Real s_part_cta[2 * FIELD_WARPS * 2], s_part_grp[2 * FIELD_WARPS * 2];
+  __shared__ __align__(8) unsigned long long s_wbar[FIELD_WARPS];
+  constexpr bool COMPACT = STAGED;
+  using Tab = FieldTab<Real, COMPACT>;
   Real *s_tab = reinterpret_cast<Real *>(s_raw);
   for (int t = threadIdx.x; t < a.n_tab; t += FIELD_THREADS)
-    FieldTab<Real>::put(s_tab, a.n_tab, t, PEND != PEND_NONE ? a.pend_told[t] : Real(0),
-                        PEND != PEND_NONE ? a.pend_tnew[t] : Real(0), IS_V ? a.theta[a.last_base + t] : Real(0));
+    Tab::put(s_tab, a.n_tab, t, PEND != PEND_NONE ? a.pend_told[t] : Real(0),
+             PEND != PEND_NONE ? a.pend_tnew[t] : Real(0), IS_V ? a.theta[a.last_base + t] : Real(0));
+  if (STAGED && (threadIdx.x & 31) == 0)
+    mbar_init(&s_wbar[threadIdx.x >> 5], 1);
   __syncthreads();
   const Real alpha = *a.alpha;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -451,9 +555,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     const Real lam = a.lambda[g], mu = a.mu[g], z = a.z[j];
     Real sq = 0, lin = 0, theta_new = theta_old;
     if (MODE != FIELD_UPDATE) {
-      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false>(a, s_tab, it.y, it.z,
-                                                                        threadIdx.x, theta_old, theta_old, alpha, sq,
-                                                                        lin);
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, false, COMPACT>(a, s_tab, it.y, it.z, threadIdx.x,
+                                                                                 theta_old, theta_old, alpha, sq, lin);
       sq = block_sum(sq, scratch);
       lin = block_sum(lin, scratch);
     }
@@ -465,9 +568,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       } else {
         theta_new = column_draw<Real, IS_V>(sq, lin, theta_old, alpha, lam, mu, z);
       }
-      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true>(a, s_tab, it.y, it.z,
-                                                                       threadIdx.x, theta_old, theta_new, alpha, sq,
-                                                                       lin);
+      field_pass<Real, IS_V, UNIT, HAS_MID, PEND, FIELD_THREADS, true, COMPACT>(a, s_tab, it.y, it.z, threadIdx.x,
+                                                                                theta_old, theta_new, alpha, sq, lin);
     }
     __syncthreads(); // every thread has read theta[j]
     if (threadIdx.x == 0)
@@ -490,7 +592,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
           given = draw_given(slot, theta_old, lam, mu, z);
         given = __shfl_sync(FULL_MASK, given, 0);
       }
-      const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_WARPS, R, false>(
+      const Real theta_new = field_column_regs<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_WARPS, R, false, COMPACT>(
           a, s_tab, it, threadIdx.x, theta_old, alpha, lam, mu, z, s_part_cta, parity, 0, warp, lane,
           given, sq, lin);
       if (MODE == FIELD_UPDATE)
@@ -518,7 +620,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
           given = draw_given(slot, theta_old, lam, mu, z);
         given = __shfl_sync(FULL_MASK, given, 0);
       }
-      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_GROUP_WARPS>(
+      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, FIELD_GROUP_WARPS, COMPACT>(
           a, s_tab, it, wig * 32 + lane, theta_old, alpha, lam, mu, z, s_part_grp, parity, grp, wig,
           lane, given, sq, lin);
       if (MODE == FIELD_UPDATE) // every warp of the group has read theta[j] before it changes
@@ -538,6 +640,32 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   const int4 *items_w = a.item + first_w;
   const int FIELD_BATCH = a.batch;
   int kb = (blockIdx.x + gridDim.x * warp) * FIELD_BATCH; // longest columns spread over the SMs
+  // STAGED: this warp's buffer (behind the table and the other warps' buffers) and its copy engine
+  constexpr bool NEED_IDX = IS_V || PEND != PEND_NONE;
+  unsigned char *w_buf = s_raw + ((static_cast<size_t>(a.n_tab) * Tab::BYTES_PER_COLUMN + 15) / 16) * 16 +
+                         static_cast<size_t>(warp) * FieldStageSize<Real>::BYTES;
+  unsigned long long *w_bar = &s_wbar[warp];
+  uint32_t w_phase = 0;
+  FieldStage<Real> stage;
+  stage.eq = reinterpret_cast<const Pair<Real> *>(w_buf);
+  stage.idx = reinterpret_cast<const int *>(w_buf + FieldStageSize<Real>::EQ_BYTES);
+  // starts the copy of the rows [lo, hi) of a column into the buffer (lane 0); an empty column copies nothing
+  auto stage_issue = [&](int lo, int hi) {
+    if (!STAGED || lane != 0 || hi <= lo)
+      return;
+    constexpr int AE = 16 / static_cast<int>(sizeof(Pair<Real>));
+    const int e0 = lo & ~(AE - 1), e1 = (hi + AE - 1) & ~(AE - 1), i0 = lo & ~3, i1 = (hi + 3) & ~3;
+    const uint32_t eb = static_cast<uint32_t>(e1 - e0) * sizeof(Pair<Real>), ib = NEED_IDX ? (i1 - i0) * 4u : 0u;
+    fence_async_smem(); // the buffer's previous contents have been read (by all lanes: __syncwarp before)
+    mbar_expect_tx(w_bar, eb + ib);
+    bulk_load(w_buf, a.eq + e0, eb, w_bar);
+    if (NEED_IDX)
+      bulk_load(w_buf + FieldStageSize<Real>::EQ_BYTES, a.tail_last + i0, ib, w_bar);
+  };
+  if (STAGED && kb < a.nW) {
+    const int4 first = __ldg(items_w + kb);
+    stage_issue(first.y, first.z);
+  }
   while (kb < a.nW) {
     int kb_next = 0;
     if (lane == 0)
@@ -557,6 +685,10 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       if (MODE == FIELD_UPDATE)
         my_given = draw_given(my_slot, my_theta, my_lam, my_mu, my_z);
     }
+    kb_next = __shfl_sync(FULL_MASK, kb_next, 0);
+    int4 next_first = make_int4(0, 0, 0, 0); // first column of this warp's next batch
+    if (STAGED && kb_next < a.nW)
+      next_first = __ldg(items_w + kb_next);
     for (int bi = 0; bi < n_batch; bi++) {
       int4 it;
       it.x = __shfl_sync(FULL_MASK, my_it.x, bi), it.y = __shfl_sync(FULL_MASK, my_it.y, bi);
@@ -566,12 +698,33 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
       const Real given = MODE == FIELD_UPDATE ? __shfl_sync(FULL_MASK, my_given, bi) : Real(0);
       const int slot = MODE == FIELD_FUSED ? 0 : __shfl_sync(FULL_MASK, my_slot, bi);
       Real sq, lin;
-      const Real theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, 1>(
-          a, s_tab, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin);
+      Real theta_new;
+      if (STAGED) {
+        // the column that follows this one in the warp's work (next in the batch, or first of the next batch)
+        const int nb = min(bi + 1, 31);
+        int n_lo = __shfl_sync(FULL_MASK, my_it.y, nb), n_hi = __shfl_sync(FULL_MASK, my_it.z, nb);
+        if (bi + 1 >= n_batch)
+          n_lo = next_first.y, n_hi = next_first.z;
+        constexpr int AE = 16 / static_cast<int>(sizeof(Pair<Real>));
+        stage.eq_row0 = it.y & ~(AE - 1), stage.idx_row0 = it.y & ~3;
+        if (it.z > it.y) { // (an empty column was not copied)
+          mbar_wait(w_bar, w_phase);
+          w_phase ^= 1;
+        }
+        auto hook = [&]() {
+          __syncwarp();
+          stage_issue(n_lo, n_hi);
+        };
+        theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, 1, COMPACT, true>(
+            a, s_tab, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin, stage, hook);
+      } else {
+        theta_new = field_column_dispatch<Real, IS_V, UNIT, HAS_MID, PEND, MODE, 1, COMPACT>(
+            a, s_tab, it, lane, theta_old, alpha, lam, mu, z, nullptr, 0, 0, 0, lane, given, sq, lin);
+      }
       if (lane == 0)
         field_finish_column<Real, MODE>(a, it.x, slot, theta_new, sq, lin);
     }
-    kb = __shfl_sync(FULL_MASK, kb_next, 0);
+    kb = kb_next;
   }
   if (MODE == FIELD_STATS)
     peer_post_when_last(a.peer);

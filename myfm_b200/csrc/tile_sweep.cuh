@@ -42,48 +42,6 @@ constexpr int TILE_MAX_TAB = 65535;         // ... and so are last-field columns
 constexpr unsigned TILE_NO_KEY = 0xffffffffu;
 constexpr uint32_t TILE_BULK_CHUNK = 32768; // bytes per bulk copy instruction
 
-// ---- TMA (1-D bulk copy) and mbarrier primitives ------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-  asm volatile("{\n"
-               ".reg .pred p;\n"
-               "WAIT_LOOP:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra WAIT_DONE;\n"
-               "bra WAIT_LOOP;\n"
-               "WAIT_DONE:\n"
-               "}" ::"r"(smem_addr(bar)),
-               "r"(parity)
-               : "memory");
-}
-// global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-// shared -> global, tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// writes made through the generic proxy (ordinary st.shared) become visible to the async proxy (TMA)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 constexpr int TILE_VEC = 128;      // slots per warp iteration of the B passes: one 16-byte load per lane
 constexpr int TILE_TEAM = 8;       // lanes per first-field column of up to TILE_TEAM_MAX rows (4 columns per warp)
 constexpr int TILE_TEAM_MAX = 256;

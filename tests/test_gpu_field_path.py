@@ -132,3 +132,21 @@ def test_wide_rank_forward_pass(engine, oracle, rank, unit, fields):
     X2.data = X2.data ** 2
     ref = w0 + Xd.dot(w) + 0.5 * ((Xd.dot(V) ** 2).sum(1) - X2.dot((V ** 2).sum(1)))
     np.testing.assert_allclose(score, ref, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", ["f32"])
+def test_staged_streaming_kernel(engine, oracle, dtype, monkeypatch):
+    """MYFM_STAGING=1: the warp class of k_field_stream reads its rows from per-warp shared-memory buffers filled
+    by TMA bulk copies (cp.async.bulk + mbarrier) one column ahead; same chain as the direct-load kernel, bit for bit."""
+    X, y, gs = movielens_like(40000, 900, 150, 4, seed=12, zipf=(0.5, 0.8))
+    a, chain = make_pair(engine, oracle, X, y, 6, dtype, group_shapes=gs)
+    monkeypatch.setenv("MYFM_STAGING", "1")
+    b, _ = make_pair(engine, oracle, X, y, 6, dtype, group_shapes=gs)
+    for it in range(4):
+        a.step(1)
+        b.step(1)
+        chain.step()
+        for xa, xb in zip(a.get_fm()[:3], b.get_fm()[:3]):
+            np.testing.assert_array_equal(xa, xb)
+        np.testing.assert_array_equal(a.get_e(), b.get_e())
+    assert_state_close(b, chain, dtype, "staged kernel, sweep 3", free_running=True)
