@@ -56,5 +56,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PYBIND_SRC = os.path.join(HERE, "pybind_binding.cpp")
+
+
+def pybind_path() -> str:
+    import sysconfig
+
+    return os.path.join(os.path.dirname(HERE), "_myfm_pybind" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind(force: bool = False) -> str:
+    """The pybind11 binding over the C ABI (myfm_b200/_myfm_pybind*.so): plain g++, links libmyfm_b200.so."""
+    import sysconfig
+
+    import pybind11
+
+    out = pybind_path()
+    lib = build()
+    if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(PYBIND_SRC),
+                                                                          os.path.getmtime(lib)):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", f"-I{pybind11.get_include()}",
+           f"-I{sysconfig.get_paths()['include']}", PYBIND_SRC, "-o", out, f"-L{HERE}", "-lmyfm_b200",
+           "-Wl,-rpath,$ORIGIN/csrc"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building the pybind11 binding")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -210,3 +210,21 @@ def test_mt19937_jump_polynomial(n):
         for i in taps.astype(np.int64):
             acc ^= words[a + i:a + i + 624]
         np.testing.assert_array_equal(acc, words[a + n:a + n + 624])
+
+
+def test_pybind_binding_builds_and_has_no_cpu_fallback():
+    """myfm_b200/csrc/pybind_binding.cpp compiles against the C ABI and, without a GPU, fails like the ctypes path."""
+    from myfm_b200 import _lib
+    from myfm_b200._myfm import ConfigBuilder
+    from myfm_b200.csrc import build
+
+    build.build_pybind()
+    from myfm_b200 import _myfm_pybind
+
+    assert _myfm_pybind.device_count() == _lib.device_count()
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    X, y = toy_matrix()
+    cfg = ConfigBuilder().set_identical_groups(X.shape[1]).set_n_iter(2).set_n_kept_samples(2).build()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _myfm_pybind.create_train_fm(2, 0.1, X, [], y, 1, cfg, lambda *a: False)
