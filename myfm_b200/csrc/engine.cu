@@ -791,6 +791,7 @@ template <typename Real> struct Trainer : TrainerBase {
     reset_graphs();
     if (rng_stream)
       cudaStreamSynchronize(rng_stream);
+    dump_peer_trace();
     if (!peer_base.empty() || peer_local)
       close_peer_exchange(peer_ok);
     if (comm)
@@ -1605,6 +1606,10 @@ template <typename Real> struct Trainer : TrainerBase {
     peer_ok = ok != 0;
     peer_error.alloc(1);
     peer_error.zero(stream);
+    if (peer_ok && std::getenv("MYFM_PEER_TRACE")) {
+      peer_trace_buf.alloc(static_cast<size_t>(PEER_TRACE_RECORDS) * PEER_TRACE_SLOTS);
+      peer_trace_buf.zero(stream);
+    }
     MYFM_CUDA(cudaStreamSynchronize(stream));
     if (!peer_ok)
       close_peer_exchange();
@@ -1661,6 +1666,7 @@ template <typename Real> struct Trainer : TrainerBase {
     }
     pv.my_posted = reinterpret_cast<unsigned long long *>(peer_local);
     pv.done = reinterpret_cast<unsigned int *>(peer_local + 16);
+    pv.trace = peer_trace_buf.p, pv.trace_cap = peer_trace_buf.p ? PEER_TRACE_RECORDS : 0;
     for (int r = 0; r < world; r++) {
       pv.stat[r] = peer_stat(r);
       pv.posted[r] = reinterpret_cast<const unsigned long long *>(peer_base[r]);
@@ -1668,6 +1674,32 @@ template <typename Real> struct Trainer : TrainerBase {
     return pv;
   }
   DevBuf<int> peer_error;
+  // MYFM_PEER_TRACE=<path prefix>: device time stamps of the last PEER_TRACE_RECORDS collectives, written to
+  // <prefix>.rank<r>.csv when the trainer is destroyed (tools/peer_timeline.py reads them).
+  static constexpr int PEER_TRACE_RECORDS = 4096;
+  DevBuf<unsigned long long> peer_trace_buf;
+  void dump_peer_trace() {
+    const char *prefix = std::getenv("MYFM_PEER_TRACE");
+    if (!prefix || !peer_trace_buf.p)
+      return;
+    std::vector<unsigned long long> t(static_cast<size_t>(PEER_TRACE_RECORDS) * PEER_TRACE_SLOTS);
+    if (cudaMemcpy(t.data(), peer_trace_buf.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return;
+    const std::string path = std::string(prefix) + ".rank" + std::to_string(my_rank) + ".csv";
+    if (FILE *f = std::fopen(path.c_str(), "w")) {
+      std::fprintf(f, "seq,stats_start,stats_posted,draw_start,draw_peers_seen,draw_done,stream_start,stream_done\n");
+      for (int r = 0; r < PEER_TRACE_RECORDS; r++) {
+        const unsigned long long *q = t.data() + static_cast<size_t>(r) * PEER_TRACE_SLOTS;
+        if (q[0] == 0)
+          continue;
+        std::fprintf(f, "%llu", q[7]);
+        for (int k = 0; k < 7; k++)
+          std::fprintf(f, ",%llu", q[k]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
+  }
 
   // ---- tile path (tile_sweep.cuh): two fields, row tiles staged in shared memory -----------------
   bool tile_path = false;

@@ -106,11 +106,29 @@ template <typename Real> struct PeerView {
   const unsigned long long *posted[PEER_MAX_RANKS]; // every rank's published sequence number
   int *error;                    // set when a peer never shows up
   unsigned long long timeout_ns; // how long peer_wait polls before it gives up (fatal)
+  // MYFM_PEER_TRACE: %globaltimer stamps per collective, PEER_TRACE_SLOTS per record, a ring of trace_cap
+  // records (nullptr: off).  The multi-GPU timeline of DESIGN.md section 5 is made from these.
+  unsigned long long *trace = nullptr;
+  int trace_cap = 0;
   // producer: where this rank's partial statistics of the NEXT collective go
   __device__ __forceinline__ Real *produce(Real *local_stat) const {
     return local_stat + ((*counter + 1) & 1) * elems;
   }
 };
+
+// Trace slots: 0 statistics kernel starts, 1 its last CTA publishes, 2 draw kernel starts, 3 every peer has
+// published, 4 draw kernel (block 0) done, 5 next streaming pass starts, 6 its block 0 is done.
+constexpr int PEER_TRACE_SLOTS = 8;
+__device__ __forceinline__ unsigned long long peer_clock_ns();
+template <typename Real>
+__device__ __forceinline__ void peer_trace(const PeerView<Real> &pv, int slot, unsigned long long ahead = 0) {
+  if (pv.world == 0 || pv.trace == nullptr)
+    return;
+  const unsigned long long seq = *pv.counter + ahead;
+  pv.trace[(seq % static_cast<unsigned long long>(pv.trace_cap)) * PEER_TRACE_SLOTS + slot] = peer_clock_ns();
+  if (slot == 0)
+    pv.trace[(seq % static_cast<unsigned long long>(pv.trace_cap)) * PEER_TRACE_SLOTS + 7] = seq;
+}
 
 // End of a producing kernel: the CTA that finishes last publishes collective *counter + 1 (no
 // separate launch).  Called by every thread of every CTA after its last statistics store.
@@ -122,6 +140,7 @@ template <typename Real> __device__ __forceinline__ void peer_post_when_last(con
     __threadfence(); // this CTA's statistics before the count
     if (atomicAdd(pv.done, 1u) == gridDim.x - 1) {
       *pv.done = 0;
+      peer_trace(pv, 1, 1);
       const unsigned long long seq = *pv.counter + 1;
       *pv.counter = seq;
       __threadfence_system();
@@ -527,6 +546,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
   constexpr bool COMPACT = STAGED;
   using Tab = FieldTab<Real, COMPACT>;
   Real *s_tab = reinterpret_cast<Real *>(s_raw);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && MODE == FIELD_FUSED)
+    peer_trace(a.peer, 5);
   for (int t = threadIdx.x; t < a.n_tab; t += FIELD_THREADS)
     Tab::put(s_tab, a.n_tab, t, PEND != PEND_NONE ? a.pend_told[t] : Real(0),
              PEND != PEND_NONE ? a.pend_tnew[t] : Real(0), IS_V ? a.theta[a.last_base + t] : Real(0));
@@ -726,6 +747,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) k_field_stream(const __grid_
     }
     kb = kb_next;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && MODE == FIELD_FUSED)
+    peer_trace(a.peer, 6);
   if (MODE == FIELD_STATS)
     peer_post_when_last(a.peer);
 }
@@ -784,23 +807,32 @@ __device__ __forceinline__ void field_publish(const FieldStatsArgs<Real> &a, int
 template <typename Real, bool IS_V>
 __global__ void __launch_bounds__(256)
     k_field_draw_last(FieldStatsArgs<Real> a, PeerView<Real> peer, const int *__restrict__ cols, int n_cols) {
+  const bool tracer = blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracer)
+    peer_trace(peer, 2);
   peer_wait(peer);
+  if (tracer)
+    peer_trace(peer, 3);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_cols)
-    return;
-  const int j = cols[slot];
-  Real sq, lin;
-  if (peer.world)
-    peer_sum(peer, slot, sq, lin);
-  else
-    sq = a.colstat[2 * slot], lin = a.colstat[2 * slot + 1];
-  field_publish_draw<Real, IS_V>(a, j, sq, lin, a.theta[j], *a.alpha);
+  if (slot < n_cols) {
+    const int j = cols[slot];
+    Real sq, lin;
+    if (peer.world)
+      peer_sum(peer, slot, sq, lin);
+    else
+      sq = a.colstat[2 * slot], lin = a.colstat[2 * slot + 1];
+    field_publish_draw<Real, IS_V>(a, j, sq, lin, a.theta[j], *a.alpha);
+  }
+  if (tracer)
+    peer_trace(peer, 4);
 }
 
 template <typename Real, bool IS_V, bool UNIT>
 __global__ void __launch_bounds__(STATS_THREADS) k_field_stats(FieldStatsArgs<Real> a) {
   __shared__ Real scratch[32];
   const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0)
+    peer_trace(a.peer, 0, 1);
   const bool cta_item = b < a.nS + a.nC;
   const int lane = threadIdx.x & 31;
   const int w = (b - a.nS - a.nC) * (STATS_THREADS / 32) + (threadIdx.x >> 5);
