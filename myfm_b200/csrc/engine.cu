@@ -749,7 +749,7 @@ template <typename Real> struct Trainer : TrainerBase {
     group.upload(cfg.group_index, stream);
     feat_ptr.upload(cfg.feat_ptr, stream);
     feat_idx.upload(cfg.feat_idx, stream);
-    partial.alloc(REDUCE_BLOCKS);
+    partial.alloc(2 * REDUCE_BLOCKS);
     scal.alloc(4);
     MYFM_CUDA(cudaStreamSynchronize(stream));
 
@@ -2529,14 +2529,31 @@ template <typename Real> struct Trainer : TrainerBase {
       f_launch = 0, f_pending_valid = false;
     }
 
-    if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
+    const bool alpha_w0_fused = cfg.task_type == MYFM_TASK_REGRESSION && cfg.fit_w0;
+    if (alpha_w0_fused) { // update_alpha + update_w0: one pass over e for both sums, one exchange, one draw kernel
+      k_reduce_e_both<Real><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
+      int n_partial = REDUCE_BLOCKS;
+      if (world > 1) {
+        k_fold_partials2<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p);
+        launched();
+        allreduce_sum(partial.p, 2);
+        n_partial = 1;
+      }
+      k_finish_alpha_w0<Real><<<1, 256, 0, stream>>>(n_partial, partial.p, partial.p + n_partial,
+                                                      static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha,
+                                                      static_cast<int>(N_global), static_cast<Real>(cfg.reg_0),
+                                                      z + L.z_w0, h.w0, scal.p);
+      k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, eq(), scal.p);
+      launched(3);
+    } else if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
       k_reduce_e<Real, 0><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
       const int n_partial = fold_over_ranks();
       k_finish_alpha<Real><<<1, 256, 0, stream>>>(n_partial, partial.p,
                                                    static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha);
       launched(2);
     }
-    if (cfg.fit_w0) { // update_w0
+    if (alpha_w0_fused) { // done above
+    } else if (cfg.fit_w0) { // update_w0
       k_reduce_e<Real, 1><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
       const int n_partial = fold_over_ranks();
       k_finish_w0<Real><<<1, 256, 0, stream>>>(n_partial, partial.p, static_cast<int>(N_global),

@@ -342,6 +342,52 @@ __global__ void __launch_bounds__(512)
     partial[blockIdx.x] = acc;
 }
 
+// Both sums in one pass over e (regression with fit_w0: update_alpha is followed by update_w0 and neither
+// changes e in between): partial[b] = block sum of e^2, partial[gridDim.x + b] = block sum of (w0 - e);
+// per thread and per block the same additions in the same order as the two separate kernels.
+template <typename Real>
+__global__ void __launch_bounds__(512)
+    k_reduce_e_both(int64_t n, const Pair<Real> *__restrict__ eq, const Real *__restrict__ w0_ptr,
+                    Real *__restrict__ partial) {
+  __shared__ Real scratch[32];
+  Real acc2 = 0, acc1 = 0;
+  const Real w0 = *w0_ptr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    Real v = eq[i].x;
+    acc2 += v * v;
+    acc1 += (w0 - v);
+  }
+  acc2 = block_sum(acc2, scratch);
+  acc1 = block_sum(acc1, scratch);
+  if (threadIdx.x == 0)
+    partial[blockIdx.x] = acc2, partial[gridDim.x + blockIdx.x] = acc1;
+}
+
+// Stage 2 of both (one block): k_finish_alpha, then k_finish_w0 with the new alpha.  part_w0: the
+// partials of (w0 - e), n_partial of them.
+template <typename Real>
+__global__ void k_finish_alpha_w0(int n_partial, const Real *__restrict__ partial, const Real *__restrict__ part_w0,
+                                  Real beta_0, const Real *__restrict__ g_std, Real *alpha_ptr, int n_train,
+                                  Real reg_0, const Real *__restrict__ z, Real *w0, Real *delta) {
+  __shared__ Real scratch[32];
+  Real acc2 = 0, acc1 = 0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x)
+    acc2 += partial[i], acc1 += part_w0[i];
+  acc2 = block_sum(acc2, scratch);
+  acc1 = block_sum(acc1, scratch);
+  if (threadIdx.x == 0) {
+    Real variance = (beta_0 + acc2) / 2;
+    const Real alpha = *g_std * (1 / variance);
+    *alpha_ptr = alpha;
+    Real lin = alpha * acc1;
+    Real quad = alpha * n_train + reg_0;
+    Real w0_new = (lin / quad) + *z / sqrt(quad);
+    *delta = (w0_new - *w0);
+    *w0 = w0_new;
+  }
+}
+
 // Stage 2 (one block): alpha ~ Gamma((alpha_0+N)/2, 2/(beta_0+sum e^2)) from a standardised
 // Gamma variate (FMTrainer.hpp:140-144).
 template <typename Real>
@@ -408,16 +454,18 @@ __global__ void __launch_bounds__(HYPER_THREADS)
   const int b = feat_ptr[g], en = feat_ptr[g + 1];
   const Real mean = mu[g + G * v];
   Real dev2 = 0, sum = 0;
-  // four independent gathers in flight per thread: the loop is latency-bound otherwise
-  for (int p0 = b + threadIdx.x; p0 < en; p0 += 4 * HYPER_THREADS) {
-    Real t[4];
+  // HYPER_UNROLL independent gathers in flight per thread: the loop is latency-bound otherwise (one block walks
+  // all features of its group; the additions happen in the same order for any unroll factor)
+  constexpr int HYPER_UNROLL = 16;
+  for (int p0 = b + threadIdx.x; p0 < en; p0 += HYPER_UNROLL * HYPER_THREADS) {
+    Real t[HYPER_UNROLL];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < HYPER_UNROLL; u++) {
       const int p = p0 + u * HYPER_THREADS;
       t[u] = p < en ? th[feat_idx[p]] : mean;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < HYPER_UNROLL; u++)
       if (p0 + u * HYPER_THREADS < en) {
         Real dev = t[u] - mean;
         dev2 += dev * dev;
@@ -750,6 +798,18 @@ template <typename Real> __global__ void k_fold_partials(int n, Real *partial) {
   __syncthreads();
   if (threadIdx.x == 0)
     partial[0] = acc;
+}
+// Two runs of n partials -> partial[0], partial[1] (one all-reduce of two scalars follows).
+template <typename Real> __global__ void k_fold_partials2(int n, Real *partial) {
+  __shared__ Real scratch[32];
+  Real acc0 = 0, acc1 = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    acc0 += partial[i], acc1 += partial[n + i];
+  acc0 = block_sum(acc0, scratch);
+  acc1 = block_sum(acc1, scratch);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    partial[0] = acc0, partial[1] = acc1;
 }
 
 // ----------------------------------------------------------------------------------------------

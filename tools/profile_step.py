@@ -19,9 +19,17 @@ ap.add_argument("--workload", default="ml10m")
 ap.add_argument("--sweeps", type=int, default=2)
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--families", action="store_true", help="per-family CUDA-event times")
+ap.add_argument("--shard", default="", help="R/N: only the rows rank R of N would hold (column partition), on one GPU")
 args = ap.parse_args()
 
 wl = bench.Workload(args.workload)
+if args.shard:  # what one rank of a row-sharded run computes, without its peers (kernel times under ncu)
+    from myfm_b200.distributed import column_partition
+    r, n = (int(v) for v in args.shard.split("/"))
+    wl.X.sort_indices()
+    rows = (column_partition(wl.X, n) == r).nonzero()[0]
+    wl.X, wl.y = wl.X[rows], wl.y[rows]
+    print(f"shard {r}/{n}: {rows.size} rows")
 with myfm_b200.engine_options(dtype=args.dtype):
     t = _TrainerHandle(wl.X, wl.blocks(), wl.y_engine, bench.CHAIN_SEED, wl.config(args.sweeps))
     t.init_fm(wl.rank, 0.1)
