@@ -263,13 +263,23 @@ template <typename Real> struct Dataset : DatasetBase {
       MYFM_CUDA(cudaGetDevice(&dev));
       MYFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       const int grid = std::min(ceil_div(static_cast<int64_t>(ceil_div(n, 32)) * 32, 256), sms * 8);
+#define MYFM_TILE5(LL, U, KPL, PAIR, FULL)                                                         \
+  k_predict_tile<Real, LL, U, KPL, PAIR, FULL><<<grid, 256, 0, stream>>>(n, X.idx.p, X.val.p, w_dev, Vt_dev, K, w0_dev, \
+                                                                         y, out, out_stride);
 #define MYFM_TILE4(LL, U, KPL)                                                                     \
-  if (out_stride == 2)                                                                             \
-    k_predict_tile<Real, LL, U, KPL, true><<<grid, 256, 0, stream>>>(n, X.idx.p, X.val.p, w_dev, Vt_dev, K, w0_dev, y,  \
-                                                                     out, out_stride);             \
-  else                                                                                             \
-    k_predict_tile<Real, LL, U, KPL, false><<<grid, 256, 0, stream>>>(n, X.idx.p, X.val.p, w_dev, Vt_dev, K, w0_dev, y, \
-                                                                      out, out_stride);
+  if (out_stride == 2) {                                                                           \
+    if (K == 32 * KPL) {                                                                           \
+      MYFM_TILE5(LL, U, KPL, true, true)                                                           \
+    } else {                                                                                       \
+      MYFM_TILE5(LL, U, KPL, true, false)                                                          \
+    }                                                                                              \
+  } else {                                                                                         \
+    if (K == 32 * KPL) {                                                                           \
+      MYFM_TILE5(LL, U, KPL, false, true)                                                          \
+    } else {                                                                                       \
+      MYFM_TILE5(LL, U, KPL, false, false)                                                         \
+    }                                                                                              \
+  }
 #define MYFM_TILE3(LL, U)                                                                          \
   if (K <= 32) {                                                                                   \
     MYFM_TILE4(LL, U, 1)                                                                           \
@@ -293,6 +303,7 @@ template <typename Real> struct Dataset : DatasetBase {
 #undef MYFM_TILE2
 #undef MYFM_TILE3
 #undef MYFM_TILE4
+#undef MYFM_TILE5
       count();
       MYFM_CUDA(cudaGetLastError());
       return;

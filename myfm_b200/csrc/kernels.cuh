@@ -234,7 +234,11 @@ __global__ void __launch_bounds__(256)
 // butterfly (one shuffle per row instead of five) and lane l finishes row l.
 // PAIR: out is the trainer's interleaved {e, q} array; both halves are written (q = 0) so that
 // whole sectors are stored.
-template <typename Real, int L, bool UNIT, int KPL, bool PAIR>
+// FULL: K == 32 * KPL exactly (K = 32, 64): no per-lane predicate, the row stride is a compile-time constant and the
+// address of a V row is one IMAD.WIDE.  The per-row term is accumulated as q^2 - s and halved once at the end
+// (scaling by a power of two commutes with every rounding of the sum): 1177 -> ~550 instructions per tile of 32
+// rows for K = 32, L = 2 — the kernel is issue-bound (profiles/r02f_predict_tile.md).
+template <typename Real, int L, bool UNIT, int KPL, bool PAIR, bool FULL>
 __global__ void __launch_bounds__(256)
     k_predict_tile(int n_rows, const int *__restrict__ idx, const Real *__restrict__ val,
                    const Real *__restrict__ w, const Real *__restrict__ Vt, int K,
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(256)
   const int lane = threadIdx.x & 31;
   const int n_tiles = (n_rows + 31) >> 5;
   const Real w0 = *w0_ptr, half = static_cast<Real>(0.5);
+  const char *vbase = reinterpret_cast<const char *>(Vt + lane);
+  const int row_bytes = (FULL ? 32 * KPL : K) * static_cast<int>(sizeof(Real));
   for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += (gridDim.x * blockDim.x) >> 5) {
     const int row = tile * 32 + lane;
     const bool valid = row < n_rows;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(256)
       x[k] = UNIT ? Real(1) : __ldcs(val + p0 + k);
       lin += x[k] * w[j[k]];
     }
-    Real part[32];
+    Real part[32]; // twice the row's pair term: sum over this lane's factors of q^2 - s
 #pragma unroll
     for (int rr = 0; rr < 32; rr++) {
       Real q[KPL], s[KPL];
@@ -267,21 +273,27 @@ __global__ void __launch_bounds__(256)
       for (int k = 0; k < L; k++) {
         const int jk = __shfl_sync(FULL_MASK, j[k], rr);
         const Real xk = UNIT ? Real(1) : __shfl_sync(FULL_MASK, x[k], rr);
-        const Real *vrow = Vt + static_cast<int64_t>(jk) * K;
+        const Real *vrow = reinterpret_cast<const Real *>(vbase + static_cast<int64_t>(jk) * row_bytes);
 #pragma unroll
         for (int u = 0; u < KPL; u++)
-          if (lane + 32 * u < K) {
-            const Real v = vrow[lane + 32 * u];
-            q[u] += xk * v;
-            s[u] += (xk * xk) * (v * v);
+          if (FULL || lane + 32 * u < K) {
+            const Real v = vrow[32 * u];
+            const Real xv = UNIT ? v : xk * v;
+            const Real xv2 = UNIT ? v * v : (xk * xk) * (v * v);
+            if (k == 0) // 0 + a = a: the first field assigns
+              q[u] = xv, s[u] = xv2;
+            else
+              q[u] += xv, s[u] += xv2;
           }
       }
       Real tot = 0;
 #pragma unroll
       for (int u = 0; u < KPL; u++)
-        if (lane + 32 * u < K) {
-          tot += (q[u] * q[u]) * half;
-          tot -= s[u] * half;
+        if (FULL || lane + 32 * u < K) {
+          if (u == 0 && FULL)
+            tot = q[u] * q[u] - s[u];
+          else
+            tot += q[u] * q[u], tot -= s[u];
         }
       part[rr] = tot;
     }
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(256)
       }
     }
     if (valid) {
-      Real t = (w0 + lin) + part[0];
+      Real t = (w0 + lin) + part[0] * half;
       if (y)
         t = t - y[row];
       if (PAIR) {
