@@ -268,6 +268,8 @@ def run_c5(args):
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     achieved = total_bytes * it_per_s / 1e9 / world
     path_name, kernel_desc = SWEEP_PATHS.get(sweep_path, (str(sweep_path), "?"))
+    if wl.rel:
+        kernel_desc += " + k_rel_sweep_smem (the relation blocks' column chain: one CTA, latency-bound, DESIGN.md 3d)"
     line = {
         "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -620,6 +622,8 @@ def run_ours(args):
     traffic, traffic_src = ncu_traffic(rank) if (sweep_path in (1, 5) and args.gpus == 1 and args.workload == "ml10m"
                                                  and dtype == "f32") else (None, None)
     path_name, kernel_desc = SWEEP_PATHS.get(sweep_path, (str(sweep_path), "?"))
+    if wl.rel:
+        kernel_desc += " + k_rel_sweep_smem (the relation blocks' column chain: one CTA, latency-bound, DESIGN.md 3d)"
     config_n_iter = 200  # the iteration count BASELINE.json's C4 is quoted on
     line = {
         "metric": "gibbs_iterations_per_sec", "value": it_per_s, "unit": "it/s", "n_gpus": args.gpus,

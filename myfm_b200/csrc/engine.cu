@@ -2225,6 +2225,7 @@ template <typename Real> struct Trainer : TrainerBase {
     MYFM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const size_t smem = 7 * static_cast<size_t>(d.S) * sizeof(Real);
     const char *no_smem = std::getenv("MYFM_REL_GLOBAL");
+    TimedSpan span(timer, stream, 0); // the block's column sweep belongs to the column-sweep family
     if (smem + 1024 <= static_cast<size_t>(dev_smem) && !(no_smem && no_smem[0] == '1')) {
       auto kernel = k_rel_sweep_smem<Real, IS_V>;
       static size_t configured = 0; // per instantiation

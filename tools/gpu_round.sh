@@ -29,9 +29,12 @@ done
 # launch list of the bench command itself (a number printed under ncu is never a bench value)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 tail -1 gpurun_out/ncu_launches.log | cut -c1-200
-# full-set capture of the hot kernels; the report stays on the box, its raw page comes back as CSV
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_field_stream|k_field_stats|k_predict_tile|k_mt_farm" -s 40 -c 6 \
+# full-set capture of the hot kernels; the reports stay on the box, their raw pages come back as CSV
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_field_stream|k_field_stats" -s 40 -c 4 \
     -o /tmp/full_$TAG -f python tools/profile_step.py --sweeps 3 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ncu -i /tmp/full_$TAG.ncu-rep --page raw --csv > gpurun_out/full_${TAG}_raw.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_predict_tile|k_mt_farm|k_group_hyper|k_reduce_e_both" -s 4 -c 5 \
+    -o /tmp/full2_$TAG -f python tools/profile_step.py --sweeps 3 > gpurun_out/ncu_full2.log 2>&1
+ncu -i /tmp/full2_$TAG.ncu-rep --page raw --csv > gpurun_out/full_${TAG}_other_raw.csv 2>/dev/null
 ls -la gpurun_out/ | tail -5
