@@ -568,9 +568,11 @@ def run_ours(args):
     stamps = []
 
     def callback(i, fm, hyper_, history):
-        _ = (fm.w0, hyper_.alpha)  # the device->host read of the sweep's result
+        _ = hyper_.alpha  # the device->host read of the sweep's result: its hyper-parameters (fetched before this call)
         stamps.append(time.perf_counter())
         return False, None
+
+    callback.observer = True  # reads `hyper` only: the next sweep may start before this host code runs
 
     if dist is not None:
         dist.barrier()
@@ -601,11 +603,11 @@ def run_ours(args):
     # Host->device: a Gibbs fit uploads its inputs (X as CSR with int64 indptr / int32 indices / f64 values, y)
     # once, inside fit(); the sweeps read nothing else from the host (the variates come from the device-side
     # mt19937).  Reported amortised over the sweeps of this fit.  Device->host per sweep: the sweep's
-    # hyper-parameters (LearningHistory) and the bias the callback reads.
+    # hyper-parameters (LearningHistory).
     upload = X.indptr.shape[0] * 8 + X.nnz * (4 + 8) + y.shape[0] * 8
     upload += sum(B.indptr.shape[0] * 8 + B.nnz * 12 + np.asarray(m).shape[0] * 8 for m, B in wl.rel)
     h2d = upload / n_total
-    d2h = (2 + 2 * G + 2 * G * rank) * real_bytes + real_bytes
+    d2h = (2 + 2 * G + 2 * G * rank) * real_bytes
     if wl.task != "regression" and args.rng == "mt19937":  # the latent draws run on the host: e both ways
         h2d += X.shape[0] * real_bytes
         d2h += X.shape[0] * real_bytes
@@ -638,7 +640,7 @@ def run_ours(args):
                                     "it_per_s_at_config_n_iter": config_n_iter / (setup_s + config_n_iter / e2e),
                                     "config_n_iter": config_n_iter},
                 "note": "value: MyFM*.fit() with host scipy/numpy buffers, wall clock between per-iteration callbacks "
-                        "(each reads the sweep's hyper-parameters and bias from the device), steady state.  "
+                        "(each reads the sweep's hyper-parameters from the device; an `observer` callback, so the next sweep is already running while it executes — what fit() does with its own progress callback), steady state.  "
                         "including_setup: the whole fit() with its one-off input upload (h2d_bytes_per_step = upload "
                         "bytes / sweeps of this fit), transposes, level schedule; measured for this fit's n_iter and "
                         "projected (setup_s + n / value) to the configuration's own n_iter"},

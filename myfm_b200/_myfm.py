@@ -10,6 +10,7 @@ that touches the training data or computes a prediction goes to the GPU through 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 import math
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -868,13 +869,25 @@ def create_train_fm(
     predictor = Predictor(rank, trainer.dim_all, int(config.task_type))
     history = LearningHistory()
     n_iter, n_kept = int(config.n_iter), int(config.n_kept_samples)
+    # A callback that only observes `hyper` / `history` (attribute `observer`: True, or a predicate of the
+    # iteration) lets the next sweep start on the device before the callback's host work: `fm` is then NOT
+    # valid inside it.  MyFM*.fit() marks its own progress-bar callback on the iterations it does not report.
+    observer = getattr(callback, "observer", False)
+    if os.environ.get("MYFM_B200_NO_RUN_AHEAD", os.environ.get("MYFM_NO_RUN_AHEAD", "0")) == "1":
+        observer = False
+    in_flight = False
     for it in range(n_iter):
-        trainer.step(1)
+        if not in_flight:
+            trainer.step(1)
+        in_flight = False
         live = _LiveFM(trainer)
         if n_iter <= it + n_kept:
             predictor.samples.append(trainer.snapshot())
         hyper = trainer.get_hyper()
         history.hypers.append(hyper)
+        if it + 1 < n_iter and (observer(it) if callable(observer) else observer):
+            trainer.step(1)
+            in_flight = True
         if callback(it, live, hyper, history):
             break
     trainer.sync()  # raises if the device flagged an error (every get_hyper() above checks as well)

@@ -179,6 +179,13 @@ class MyFMBase(Generic[FM, Hyper, Predictor, History], ABC):
                 pbar.update(1)
                 return should_stop
 
+            # the default callback touches neither `fm` nor the device between its status lines: the next
+            # sweep may start before it runs (create_train_fm); a user's callback says so itself (`observer`)
+            if callback is None:
+                wrapped.observer = lambda i: bool(i % callback_default_freq)
+            else:
+                wrapped.observer = getattr(callback, "observer", False)
+
             self.predictor_, self.history_ = self._train_core(
                 self.rank, self.init_stdev, X, X_rel, y, self.random_seed, config, wrapped)
 

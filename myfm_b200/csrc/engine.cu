@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 
@@ -419,6 +420,16 @@ struct TrainerBase {
   int dtype = MYFM_DTYPE_F32;
 };
 
+// NCCL communicators by (unique id, world, rank); see the Trainer constructor.
+inline std::mutex &shared_comm_mutex() {
+  static std::mutex m;
+  return m;
+}
+inline std::map<std::string, ncclComm_t> &shared_comms() {
+  static std::map<std::string, ncclComm_t> *cache = new std::map<std::string, ncclComm_t>(); // outlives static destruction
+  return *cache;
+}
+
 template <typename Real> struct DevRelationTrain {
   DevCs<Real> Bt; // CSC of the block
   DevBuf<int> seg_ptr, seg_rows;
@@ -492,6 +503,10 @@ template <typename Real> struct Trainer : TrainerBase {
   DevBuf<Real> scal;           // [0] = w0 delta
   DevBuf<Real> partial;        // grid-reduction partials
   DevBuf<int> group, feat_ptr, feat_idx;
+  int hyper_chunks = 0;
+  DevBuf<int> hyper_chunk_group, hyper_chunk_begin;
+  DevBuf<Real> hyper_chunk_sums;
+  DevBuf<unsigned int> hyper_done;
 
   MtStream<Real> rng;
   // MYFM_RNG_PHILOX: the per-row latent draws of classification / ordered probit run on the device
@@ -760,9 +775,21 @@ template <typename Real> struct Trainer : TrainerBase {
     group.upload(cfg.group_index, stream);
     feat_ptr.upload(cfg.feat_ptr, stream);
     feat_idx.upload(cfg.feat_idx, stream);
+    { // chunks of the group hyper-parameter reduction (k_group_hyper)
+      std::vector<int> cg, cb;
+      for (int g = 0; g < G; g++) {
+        const int b = cfg.feat_ptr[g], en = cfg.feat_ptr[g + 1];
+        for (int p = b; p < en || p == b; p += HYPER_CHUNK)
+          cg.push_back(g), cb.push_back(p);
+      }
+      hyper_chunks = static_cast<int>(cg.size());
+      hyper_chunk_group.upload(cg, stream);
+      hyper_chunk_begin.upload(cb, stream);
+    }
     partial.alloc(2 * REDUCE_BLOCKS);
     scal.alloc(4);
     MYFM_CUDA(cudaStreamSynchronize(stream));
+    tick("targets, groups, buffers");
 
     N_global = world > 1 ? o.n_rows_global : N;
     if (world > 1) {
@@ -771,7 +798,23 @@ template <typename Real> struct Trainer : TrainerBase {
       NcclApi &nccl = NcclApi::get();
       ncclUniqueId id;
       std::memcpy(&id, o.nccl_unique_id, sizeof(id));
-      nccl.check(nccl.CommInitRank(&comm, world, id, o.rank), "ncclCommInitRank");
+      // One communicator per (ncclUniqueId, world, rank) and process: trainers made from the same id (the same
+      // ShardContext) share it — creating one and running its first collective costs 0.6 s on 2 GPUs and more on
+      // 8, several seconds the first time in a process.  Shared communicators live until the process exits.
+      {
+        std::string key(reinterpret_cast<const char *>(o.nccl_unique_id), sizeof(id));
+        key += ":" + std::to_string(world) + ":" + std::to_string(o.rank);
+        std::lock_guard<std::mutex> lock(shared_comm_mutex());
+        auto &cache = shared_comms();
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+          nccl.check(nccl.CommInitRank(&comm, world, id, o.rank), "ncclCommInitRank");
+          cache.emplace(key, comm);
+        } else {
+          comm = it->second;
+        }
+      }
+      tick("ncclCommInitRank (or the shared communicator)");
       // every rank must take the same schedule: the field path only if every shard qualifies
       DevBuf<int> flag(1);
       const int mine = field_path ? 1 : 0;
@@ -782,9 +825,12 @@ template <typename Real> struct Trainer : TrainerBase {
       MYFM_CUDA(cudaStreamSynchronize(stream));
       field_path = all != 0;
       my_rank = o.rank;
+      tick("first all-reduce (schedule agreement)");
       if (field_path) {
         setup_exclusive_level0();
+        tick("rank-exclusive first field");
         setup_peer_exchange();
+        tick("peer-memory exchange (cudaIpc)");
       }
     }
     // Gamma shapes are data independent (FMTrainer.hpp:140,157)
@@ -805,8 +851,7 @@ template <typename Real> struct Trainer : TrainerBase {
     dump_peer_trace();
     if (!peer_base.empty() || peer_local)
       close_peer_exchange(peer_ok);
-    if (comm)
-      NcclApi::get().CommDestroy(comm);
+    comm = nullptr; // shared with the process (shared_comms): never destroyed here
     for (auto *evs : {z_copied, z_ready, z_free})
       for (int k = 0; k < 2; k++)
         if (evs[k])
@@ -841,6 +886,9 @@ template <typename Real> struct Trainer : TrainerBase {
     rng.init_weights(Vh.data(), Vh.size(), wh.data(), wh.size(), &w0h, static_cast<Real>(init_std));
     V.alloc(Vh.size());
     Vt.alloc(Vh.size());
+    hyper_chunk_sums.alloc(2 * static_cast<size_t>(std::max(1, hyper_chunks)) * std::max(1, K));
+    hyper_done.alloc(static_cast<size_t>(std::max(1, G)) * std::max(1, K));
+    hyper_done.zero(stream);
     V.upload(Vh, stream);
     w.upload(wh, stream);
     if (Vh.size()) {
@@ -862,6 +910,10 @@ template <typename Real> struct Trainer : TrainerBase {
     {
       const char *no_graph = std::getenv("MYFM_NO_GRAPH");
       use_graphs = !(no_graph && no_graph[0] == '1');
+    }
+    if (std::getenv("MYFM_PEER_TRACE") && !phase_trace_buf.p) { // sweep-phase stamps (any number of GPUs)
+      phase_trace_buf.alloc(static_cast<size_t>(PHASE_TRACE_RECORDS) * PEER_TRACE_SLOTS + 1);
+      phase_trace_buf.zero(stream);
     }
     if (field_path || tile_path)
       f_sched.alloc(2 * (static_cast<size_t>(K) + 2));
@@ -1546,17 +1598,16 @@ template <typename Real> struct Trainer : TrainerBase {
   void merge_owned() {
     if (!f_exclusive)
       return;
-    const int64_t n_v = D_all * static_cast<int64_t>(K);
-    k_mask_owned<Real><<<ceil_div(D_all, 256), 256, 0, stream>>>(D_all, 1, f_owner.p, my_rank, w.p);
-    allreduce_sum(w.p, D_all);
-    launched();
-    if (n_v) {
-      k_mask_owned<Real><<<ceil_div(n_v, 256), 256, 0, stream>>>(D_all, K, f_owner.p, my_rank, V.p);
-      allreduce_sum(V.p, n_v);
-      k_transpose_V<Real><<<ceil_div(n_v, 256), 256, 0, stream>>>(D_all, K, V.p, Vt.p);
-      launched(2);
-    }
+    const int64_t n_all = D_all * static_cast<int64_t>(K + 1);
+    if (merge_pack.n < static_cast<size_t>(n_all))
+      merge_pack.alloc(static_cast<size_t>(n_all));
+    k_merge_pack<Real><<<ceil_div(n_all, 256), 256, 0, stream>>>(D_all, K, f_owner.p, my_rank, w.p, V.p, merge_pack.p);
+    allreduce_sum(merge_pack.p, static_cast<size_t>(n_all));
+    k_merge_unpack<Real><<<ceil_div(std::max<int64_t>(D_all, D_all * K), 256), 256, 0, stream>>>(D_all, K, merge_pack.p,
+                                                                                                   w.p, V.p, Vt.p);
+    launched(3);
   }
+  DevBuf<Real> merge_pack; // [w | V] of the owned columns, summed over the ranks in place
 
   // Maps every rank's statistics buffer into this process (cudaIpc over the NVLink / NVSwitch
   // fabric of one node).  Collective; any failure on any rank leaves every rank on NCCL.
@@ -1620,6 +1671,7 @@ template <typename Real> struct Trainer : TrainerBase {
     if (peer_ok && std::getenv("MYFM_PEER_TRACE")) {
       peer_trace_buf.alloc(static_cast<size_t>(PEER_TRACE_RECORDS) * PEER_TRACE_SLOTS);
       peer_trace_buf.zero(stream);
+
     }
     MYFM_CUDA(cudaStreamSynchronize(stream));
     if (!peer_ok)
@@ -1688,10 +1740,40 @@ template <typename Real> struct Trainer : TrainerBase {
   // MYFM_PEER_TRACE=<path prefix>: device time stamps of the last PEER_TRACE_RECORDS collectives, written to
   // <prefix>.rank<r>.csv when the trainer is destroyed (tools/peer_timeline.py reads them).
   static constexpr int PEER_TRACE_RECORDS = 4096;
+  static constexpr int PHASE_TRACE_RECORDS = 512;
   DevBuf<unsigned long long> peer_trace_buf;
+  DevBuf<unsigned long long> phase_trace_buf; // [PHASE_TRACE_RECORDS][PEER_TRACE_SLOTS] + the sweep counter
+  // phases: 0 sweep starts, 1 alpha / w0 drawn, 2 lambda_w / mu_w drawn, 3 w swept, 4 lambda_V / mu_V drawn,
+  // 5 V swept, 6 owned columns merged, 7 e refreshed
+  void stamp_phase(int slot) {
+    if (!phase_trace_buf.p)
+      return;
+    k_trace_stamp<<<1, 1, 0, stream>>>(phase_trace_buf.p, phase_trace_buf.p + static_cast<size_t>(PHASE_TRACE_RECORDS) * PEER_TRACE_SLOTS,
+                                      PHASE_TRACE_RECORDS, slot);
+  }
   void dump_peer_trace() {
     const char *prefix = std::getenv("MYFM_PEER_TRACE");
-    if (!prefix || !peer_trace_buf.p)
+    if (!prefix)
+      return;
+    if (phase_trace_buf.p) {
+      std::vector<unsigned long long> ph(static_cast<size_t>(PHASE_TRACE_RECORDS) * PEER_TRACE_SLOTS);
+      if (cudaMemcpy(ph.data(), phase_trace_buf.p, ph.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        const std::string ppath = std::string(prefix) + ".phases.rank" + std::to_string(my_rank) + ".csv";
+        if (FILE *f = std::fopen(ppath.c_str(), "w")) {
+          std::fprintf(f, "sweep_start,alpha_w0,hyper_w,w_swept,hyper_V,V_swept,merged,e_refreshed\n");
+          for (int r = 0; r < PHASE_TRACE_RECORDS; r++) {
+            const unsigned long long *q = ph.data() + static_cast<size_t>(r) * PEER_TRACE_SLOTS;
+            if (q[0] == 0 || q[7] == 0)
+              continue;
+            for (int k = 0; k < 8; k++)
+              std::fprintf(f, k ? ",%llu" : "%llu", q[k]);
+            std::fprintf(f, "\n");
+          }
+          std::fclose(f);
+        }
+      }
+    }
+    if (!peer_trace_buf.p)
       return;
     std::vector<unsigned long long> t(static_cast<size_t>(PEER_TRACE_RECORDS) * PEER_TRACE_SLOTS);
     if (cudaMemcpy(t.data(), peer_trace_buf.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -2541,20 +2623,29 @@ template <typename Real> struct Trainer : TrainerBase {
       f_launch = 0, f_pending_valid = false;
     }
 
+    stamp_phase(0);
     const bool alpha_w0_fused = cfg.task_type == MYFM_TASK_REGRESSION && cfg.fit_w0;
     if (alpha_w0_fused) { // update_alpha + update_w0: one pass over e for both sums, one exchange, one draw kernel
       k_reduce_e_both<Real><<<REDUCE_BLOCKS, 512, 0, stream>>>(N, eq(), h.w0, partial.p);
       int n_partial = REDUCE_BLOCKS;
-      if (world > 1) {
-        k_fold_partials2<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p);
+      if (world > 1 && peer_ok) { // the two sums over the ranks through the peer-memory exchange
+        k_fold_partials2_peer<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p, peer_view(), peer_stat(my_rank));
+        k_finish_alpha_w0_peer<Real><<<1, 32, 0, stream>>>(peer_view(), static_cast<Real>(cfg.beta_0), z + L.g_alpha,
+                                                            h.alpha, static_cast<int>(N_global),
+                                                            static_cast<Real>(cfg.reg_0), z + L.z_w0, h.w0, scal.p);
         launched();
-        allreduce_sum(partial.p, 2);
-        n_partial = 1;
+      } else {
+        if (world > 1) {
+          k_fold_partials2<Real><<<1, 256, 0, stream>>>(REDUCE_BLOCKS, partial.p);
+          launched();
+          allreduce_sum(partial.p, 2);
+          n_partial = 1;
+        }
+        k_finish_alpha_w0<Real><<<1, 256, 0, stream>>>(n_partial, partial.p, partial.p + n_partial,
+                                                        static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha,
+                                                        static_cast<int>(N_global), static_cast<Real>(cfg.reg_0),
+                                                        z + L.z_w0, h.w0, scal.p);
       }
-      k_finish_alpha_w0<Real><<<1, 256, 0, stream>>>(n_partial, partial.p, partial.p + n_partial,
-                                                      static_cast<Real>(cfg.beta_0), z + L.g_alpha, h.alpha,
-                                                      static_cast<int>(N_global), static_cast<Real>(cfg.reg_0),
-                                                      z + L.z_w0, h.w0, scal.p);
       k_add_scalar<Real><<<REDUCE_BLOCKS, 256, 0, stream>>>(N, eq(), scal.p);
       launched(3);
     } else if (cfg.task_type == MYFM_TASK_REGRESSION) { // update_alpha
@@ -2576,27 +2667,35 @@ template <typename Real> struct Trainer : TrainerBase {
     } else {
       MYFM_CUDA(cudaMemsetAsync(h.w0, 0, sizeof(Real), stream));
     }
+    stamp_phase(1);
     if (G) { // update_lambda_w, update_mu_w
-      k_group_hyper<Real><<<G, HYPER_THREADS, 0, stream>>>(G, feat_ptr.p, feat_idx.p, w.p, 0, h.mu_w, h.lambda_w,
-                                                 z + L.g_lw, z + L.z_mw, static_cast<Real>(cfg.beta_0),
-                                                 static_cast<Real>(cfg.gamma_0), static_cast<Real>(cfg.mu_0));
+      k_group_hyper<Real><<<hyper_chunks, HYPER_THREADS, 0, stream>>>(
+          G, hyper_chunks, hyper_chunk_group.p, hyper_chunk_begin.p, feat_ptr.p, feat_idx.p, w.p, 0, h.mu_w, h.lambda_w,
+          z + L.g_lw, z + L.z_mw, static_cast<Real>(cfg.beta_0), static_cast<Real>(cfg.gamma_0),
+          static_cast<Real>(cfg.mu_0), hyper_chunk_sums.p, hyper_done.p);
       launched();
     }
+    stamp_phase(2);
     update_w(L.z_w >= 0 ? z + L.z_w : nullptr);
+    stamp_phase(3);
     if (G && K) { // update_lambda_V, update_mu_V
-      k_group_hyper<Real><<<G * K, HYPER_THREADS, 0, stream>>>(G, feat_ptr.p, feat_idx.p, V.p, D_all, h.mu_V,
-                                                     h.lambda_V, z + L.g_lV, z + L.z_mV,
-                                                     static_cast<Real>(cfg.beta_0), static_cast<Real>(cfg.gamma_0),
-                                                     static_cast<Real>(cfg.mu_0));
+      k_group_hyper<Real><<<hyper_chunks * K, HYPER_THREADS, 0, stream>>>(
+          G, hyper_chunks, hyper_chunk_group.p, hyper_chunk_begin.p, feat_ptr.p, feat_idx.p, V.p, D_all, h.mu_V,
+          h.lambda_V, z + L.g_lV, z + L.z_mV, static_cast<Real>(cfg.beta_0), static_cast<Real>(cfg.gamma_0),
+          static_cast<Real>(cfg.mu_0), hyper_chunk_sums.p, hyper_done.p);
       launched();
     }
+    stamp_phase(4);
     update_V(z + L.z_V);
+    stamp_phase(5);
     merge_owned();
+    stamp_phase(6);
     f_pending_valid = false; // update_e overwrites e: the last vector's pending update is dropped
     { // update_e
       TimedSpan span(timer, stream, 2);
       data.predict(w.p, Vt.p, K, h.w0, cfg.task_type == MYFM_TASK_REGRESSION ? y.p : nullptr, e_ptr(), 2);
     }
+    stamp_phase(7);
   }
 
   // update_all (BaseFMTrainer.hpp:135-152)

@@ -130,6 +130,16 @@ __device__ __forceinline__ void peer_trace(const PeerView<Real> &pv, int slot, u
     pv.trace[(seq % static_cast<unsigned long long>(pv.trace_cap)) * PEER_TRACE_SLOTS + 7] = seq;
 }
 
+// MYFM_PEER_TRACE, phases of a sweep outside the column exchange: a one-thread kernel between the phases stamps
+// phase[(sweep % cap) * PEER_TRACE_SLOTS + slot]; slot 0 also advances the sweep counter.
+__global__ void k_trace_stamp(unsigned long long *phase, unsigned long long *sweep_counter, int cap, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (slot == 0)
+    *sweep_counter += 1;
+  phase[(*sweep_counter % static_cast<unsigned long long>(cap)) * PEER_TRACE_SLOTS + slot] = t;
+}
+
 // End of a producing kernel: the CTA that finishes last publishes collective *counter + 1 (no
 // separate launch).  Called by every thread of every CTA after its last statistics store.
 template <typename Real> __device__ __forceinline__ void peer_post_when_last(const PeerView<Real> &pv) {
@@ -196,6 +206,40 @@ template <typename Real> __device__ __forceinline__ void peer_sum(const PeerView
   for (int r = 0; r < PEER_MAX_RANKS; r++)
     if (r < pv.world)
       sq += v[r].x, lin += v[r].y;
+}
+
+// update_alpha + update_w0 on row shards over the same exchange (instead of an NCCL all-reduce of two scalars):
+// one block folds this rank's block partials (k_reduce_e_both) into slot 0 of its statistics buffer and
+// publishes; the draw kernel waits for every rank and adds the pairs in rank order.
+template <typename Real> __global__ void k_fold_partials2_peer(int n, const Real *__restrict__ partial, PeerView<Real> pv, Real *peer_local) {
+  __shared__ Real scratch[32];
+  Real acc0 = 0, acc1 = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    acc0 += partial[i], acc1 += partial[n + i];
+  acc0 = block_sum(acc0, scratch);
+  acc1 = block_sum(acc1, scratch);
+  if (threadIdx.x == 0) {
+    Real *out = pv.produce(peer_local);
+    out[0] = acc0, out[1] = acc1;
+  }
+  peer_post_when_last(pv);
+}
+template <typename Real>
+__global__ void k_finish_alpha_w0_peer(PeerView<Real> pv, Real beta_0, const Real *__restrict__ g_std, Real *alpha_ptr,
+                                       int n_train, Real reg_0, const Real *__restrict__ z, Real *w0, Real *delta) {
+  peer_wait(pv);
+  if (threadIdx.x == 0) {
+    Real acc2, acc1;
+    peer_sum(pv, 0, acc2, acc1);
+    Real variance = (beta_0 + acc2) / 2;
+    const Real alpha = *g_std * (1 / variance);
+    *alpha_ptr = alpha;
+    Real lin = alpha * acc1;
+    Real quad = alpha * n_train + reg_0;
+    Real w0_new = (lin / quad) + *z / sqrt(quad);
+    *delta = (w0_new - *w0);
+    *w0 = w0_new;
+  }
 }
 
 template <typename Real> struct FieldStreamArgs {

@@ -453,41 +453,60 @@ __global__ void __launch_bounds__(256)
 //              lin = lambda_g (gamma_0 mu_0 + sum theta)
 // feat_ptr/feat_idx: features of each group, ascending.
 // ----------------------------------------------------------------------------------------------
-constexpr int HYPER_THREADS = 1024;
+// The features of a group are cut into chunks of HYPER_CHUNK (host: chunk_group / chunk_begin, one entry per
+// chunk, groups in order; an empty group still owns one chunk); a block sums one chunk for one vector, the
+// block of a (group, vector) that finishes last adds the chunk sums in chunk order (deterministic) and draws.
+// One block per (group, vector) walked 70 k features of the C4 workload in ~60 us of dependent latencies.
+constexpr int HYPER_THREADS = 256;
+constexpr int HYPER_UNROLL = 16;
+constexpr int HYPER_CHUNK = HYPER_THREADS * HYPER_UNROLL;
 template <typename Real>
 __global__ void __launch_bounds__(HYPER_THREADS)
-    k_group_hyper(int G, const int *__restrict__ feat_ptr, const int *__restrict__ feat_idx,
+    k_group_hyper(int G, int n_chunks, const int *__restrict__ chunk_group, const int *__restrict__ chunk_begin,
+                  const int *__restrict__ feat_ptr, const int *__restrict__ feat_idx,
                   const Real *__restrict__ theta, int64_t theta_stride, Real *mu, Real *lambda,
                   const Real *__restrict__ g_std, const Real *__restrict__ z, Real beta_0,
-                  Real gamma_0, Real mu_0) {
+                  Real gamma_0, Real mu_0, Real *__restrict__ chunk_sums, unsigned int *__restrict__ done) {
   __shared__ Real scratch[32];
-  const int g = blockIdx.x % G, v = blockIdx.x / G;
+  const int c = blockIdx.x % n_chunks, v = blockIdx.x / n_chunks;
+  const int g = chunk_group[c];
   const Real *th = theta + theta_stride * v;
-  const int b = feat_ptr[g], en = feat_ptr[g + 1];
+  const int b = chunk_begin[c], en = min(feat_ptr[g + 1], b + HYPER_CHUNK);
   const Real mean = mu[g + G * v];
   Real dev2 = 0, sum = 0;
-  // HYPER_UNROLL independent gathers in flight per thread: the loop is latency-bound otherwise (one block walks
-  // all features of its group; the additions happen in the same order for any unroll factor)
-  constexpr int HYPER_UNROLL = 16;
-  for (int p0 = b + threadIdx.x; p0 < en; p0 += HYPER_UNROLL * HYPER_THREADS) {
-    Real t[HYPER_UNROLL];
+  Real t[HYPER_UNROLL];
 #pragma unroll
-    for (int u = 0; u < HYPER_UNROLL; u++) {
-      const int p = p0 + u * HYPER_THREADS;
-      t[u] = p < en ? th[feat_idx[p]] : mean;
-    }
-#pragma unroll
-    for (int u = 0; u < HYPER_UNROLL; u++)
-      if (p0 + u * HYPER_THREADS < en) {
-        Real dev = t[u] - mean;
-        dev2 += dev * dev;
-        sum += t[u];
-      }
+  for (int u = 0; u < HYPER_UNROLL; u++) { // all gathers in flight before the first add
+    const int p = b + threadIdx.x + u * HYPER_THREADS;
+    t[u] = p < en ? th[feat_idx[p]] : mean;
   }
+#pragma unroll
+  for (int u = 0; u < HYPER_UNROLL; u++)
+    if (b + threadIdx.x + u * HYPER_THREADS < en) {
+      Real dev = t[u] - mean;
+      dev2 += dev * dev;
+      sum += t[u];
+    }
   dev2 = block_sum(dev2, scratch);
   sum = block_sum(sum, scratch);
   if (threadIdx.x == 0) {
-    const int n_g = en - b;
+    const int first = feat_ptr[g], n_g = feat_ptr[g + 1] - first;
+    const int chunks_g = max(1, (n_g + HYPER_CHUNK - 1) / HYPER_CHUNK);
+    if (chunks_g > 1) {
+      Real *mine = chunk_sums + 2 * (static_cast<size_t>(v) * n_chunks + c);
+      __stcg(mine, dev2), __stcg(mine + 1, sum);
+      __threadfence();
+      if (atomicAdd(done + g + G * v, 1u) != static_cast<unsigned int>(chunks_g - 1))
+        return;
+      __threadfence();
+      done[g + G * v] = 0; // ready for the next launch
+      const int c0 = c - (b - first) / HYPER_CHUNK; // the group's first chunk
+      dev2 = 0, sum = 0;
+      for (int k = 0; k < chunks_g; k++) {
+        const Real *part = chunk_sums + 2 * (static_cast<size_t>(v) * n_chunks + c0 + k);
+        dev2 += __ldcg(part), sum += __ldcg(part + 1);
+      }
+    }
     Real beta = beta_0 + dev2;
     Real lam = g_std[g + G * v] * (2 / beta);
     lambda[g + G * v] = lam;
@@ -1277,6 +1296,35 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Merge of the owned columns (row shards with a rank-exclusive first field): pack = [w | V] with the entries of
+// columns another rank owns zeroed, so that ONE all-reduce over the ranks leaves the complete sample; unpack
+// writes it back to w, V and the feature-major mirror Vt.  t runs over D * (K + 1) entries.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_merge_pack(int64_t D, int K, const int *__restrict__ owner, int my_rank, const Real *__restrict__ w,
+                 const Real *__restrict__ V, Real *__restrict__ pack) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t < D * (K + 1)) {
+    const bool mine = owner[t % D] == my_rank;
+    pack[t] = mine ? (t < D ? w[t] : V[t - D]) : Real(0);
+  }
+}
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    k_merge_unpack(int64_t D, int K, const Real *__restrict__ pack, Real *__restrict__ w, Real *__restrict__ V,
+                   Real *__restrict__ Vt) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t < D)
+    w[t] = pack[t];
+  if (t < D * K) { // t as an index of Vt: coalesced writes of Vt, strided reads of the pack
+    const int64_t j = t / K;
+    const int r = static_cast<int>(t % K);
+    const Real v = pack[D + j + D * r];
+    Vt[t] = v;
+    V[j + D * r] = v;
+  }
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256) k_fill_strided(int64_t n, Real *p, int stride, Real v) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -1322,16 +1370,6 @@ __global__ void __launch_bounds__(256)
     prev = cdf;
   }
   out[static_cast<size_t>(i) * (n_cpt + 1) + n_cpt] += 1 - prev;
-}
-
-// theta[j + D * r] = 0 unless this rank owns feature j (row shards with rank-exclusive level-0
-// columns: the sum over the ranks then rebuilds the complete vector exactly)
-template <typename Real>
-__global__ void __launch_bounds__(256)
-    k_mask_owned(int64_t D, int K, const int *__restrict__ owner, int my_rank, Real *__restrict__ theta) {
-  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (t < D * K && owner[t % D] != my_rank)
-    theta[t] = 0;
 }
 
 // widening copy for the getters (the boundary speaks float64)

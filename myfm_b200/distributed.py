@@ -109,23 +109,24 @@ class ShardContext:
     nccl_unique_id: Optional[bytes]
     column_level: np.ndarray
     group: object = None
-    _id_used: bool = False
     rows: Optional[np.ndarray] = None  # global indices of this rank's rows (set by shard())
 
     @contextlib.contextmanager
     def options(self, **kwargs) -> Iterator[None]:
-        """engine_options(...) carrying this shard's description.  Collective when NCCL is in use:
-        every trainer needs its own communicator, so every use after the first fetches a fresh
-        ncclUniqueId from rank 0 (create one trainer per `with` block)."""
-        uid = self.nccl_unique_id
-        if uid is not None:
-            if self._id_used:
-                uid = _fresh_unique_id(self.group)
-            self._id_used = True
+        """engine_options(...) carrying this shard's description.  Every trainer created under it uses the
+        SAME NCCL communicator (the engine keeps one per ncclUniqueId and process: creating a communicator
+        and running its first collective costs from 0.6 s on 2 GPUs to seconds on 8), so trainers of one
+        context must be created, stepped and dropped in the same order on every rank.  `fresh_communicator()`
+        gives the context a new id (collective) when an independent communicator is wanted."""
         with engine_options(world_size=self.world_size, rank=self.rank, row_offset=self.row_offset,
-                            n_rows_global=self.n_rows_global, nccl_unique_id=uid,
+                            n_rows_global=self.n_rows_global, nccl_unique_id=self.nccl_unique_id,
                             column_level=self.column_level, row_ids=self.rows, **kwargs):
             yield
+
+    def fresh_communicator(self) -> None:
+        """Collective: the next trainers of this context get a new communicator."""
+        if self.nccl_unique_id is not None:
+            self.nccl_unique_id = _fresh_unique_id(self.group)
 
 
 def context(X_local, row_offset: int, n_rows_global: int, group=None, with_nccl: bool = True) -> ShardContext:

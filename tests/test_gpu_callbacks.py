@@ -79,3 +79,39 @@ def test_ordered_probit_callback_on_device(engine):
                                                                  group_shapes=gs, callback=_both(dev, host))
         _compare(dev, host, n_iter)
         np.testing.assert_allclose(fm.predict_proba(Xte), dev.predictions / n_iter, rtol=1e-7, atol=1e-12)
+
+
+def test_observer_callback_runs_the_same_chain(engine):
+    """create_train_fm starts the next sweep before an `observer` callback runs (myfm_b200/_myfm.py): the chain,
+    its history, the kept samples and an early stop are those of the plain loop."""
+    X, y, gs = movielens_like(6000, 80, 40, 3, seed=32)
+
+    def fit(observer, stop_at=None):
+        seen = []
+
+        def callback(i, fm, hyper, history):
+            seen.append((i, hyper.alpha, len(history.hypers)))
+            return (stop_at is not None and i == stop_at), None
+
+        callback.observer = observer
+        with engine.engine_options(dtype="f64"):
+            model = engine.MyFMRegressor(rank=4, random_seed=5).fit(X, y, n_iter=12, n_kept_samples=5,
+                                                                    group_shapes=gs, callback=callback)
+        return model, seen
+
+    plain, seen_plain = fit(False)
+    ahead, seen_ahead = fit(True)
+    odd, seen_odd = fit(lambda i: i % 2 == 1)
+    assert seen_plain == seen_ahead == seen_odd and len(seen_plain) == 12
+    for other in (ahead, odd):
+        np.testing.assert_array_equal(plain.predict(X[:500]), other.predict(X[:500]))
+        assert [h.alpha for h in plain.history_.hypers] == [h.alpha for h in other.history_.hypers]
+    # early stop: the callbacks seen and the samples kept are the same (one sweep ran ahead, unobserved)
+    stop_plain, s1 = fit(False, stop_at=9)
+    stop_ahead, s2 = fit(True, stop_at=9)
+    assert s1 == s2 and len(s1) == 10
+    np.testing.assert_array_equal(stop_plain.predict(X[:500]), stop_ahead.predict(X[:500]))
+    # fit()'s own progress callback is an observer between its status lines
+    with engine.engine_options(dtype="f64"):
+        default = engine.MyFMRegressor(rank=4, random_seed=5).fit(X, y, n_iter=12, n_kept_samples=5, group_shapes=gs)
+    np.testing.assert_array_equal(plain.predict(X[:500]), default.predict(X[:500]))

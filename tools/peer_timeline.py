@@ -19,7 +19,7 @@ def main():
     prefix = sys.argv[1]
     skip = int(sys.argv[sys.argv.index("--skip") + 1]) if "--skip" in sys.argv else 200
     files = sorted(glob.glob(prefix + ".rank*.csv"))
-    if not files:
+    if not files and not glob.glob(prefix + ".phases.rank*.csv"):
         raise SystemExit("no trace files at " + prefix)
     print("| rank | records | gather | gap1 | wait | draw | gap2 | stream | gap3 | period |")
     print("|---|---|---|---|---|---|---|---|---|---|")
@@ -38,6 +38,22 @@ def main():
         rank = path.rsplit(".rank", 1)[1].split(".")[0]
         print(f"| {rank} | {int(ok.sum())} | " + " | ".join(cells) + " |")
     print("\n(median / 90th percentile, microseconds; gaps include the rest of the sweep where a record is the last of its sweep)")
+    phase_files = sorted(glob.glob(prefix + ".phases.rank*.csv"))
+    if phase_files:
+        names = ["alpha + w0", "lambda_w, mu_w", "w sweep", "lambda_V, mu_V", "V sweep", "merge of owned columns",
+                 "e refresh", "to the next sweep's start", "sweep"]
+        print("\nPhases of a sweep (median us):\n\n| rank | sweeps | " + " | ".join(names) + " |")
+        print("|---|---|" + "---|" * len(names))
+        for path in phase_files:
+            t = np.loadtxt(path, delimiter=",", skiprows=1, dtype=np.float64, ndmin=2)
+            t = t[np.argsort(t[:, 0])][3:]
+            d = np.diff(t, axis=1) / 1e3
+            nxt = (np.roll(t[:, 0], -1) - t[:, 7])[:-1] / 1e3
+            whole = np.diff(t[:, 0]) / 1e3
+            ok = whole < 5 * np.median(whole)
+            cells = [f"{np.median(d[:, k]):.0f}" for k in range(7)] + [f"{np.median(nxt[ok]):.0f}", f"{np.median(whole[ok]):.0f}"]
+            rank = path.rsplit(".rank", 1)[1].split(".")[0]
+            print(f"| {rank} | {t.shape[0]} | " + " | ".join(cells) + " |")
 
 
 if __name__ == "__main__":
