@@ -620,7 +620,8 @@ def run_ours(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bytes_["sweeps"] * args.steps / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else None
+    # per GPU: every rank sweeps 1/N of the rows, and `peak` is one GPU's
+    achieved = bytes_["sweeps"] / args.gpus * args.steps / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else None
     traffic, traffic_src = ncu_traffic(rank) if (sweep_path in (1, 5) and args.gpus == 1 and args.workload == "ml10m"
                                                  and dtype == "f32") else (None, None)
     path_name, kernel_desc = SWEEP_PATHS.get(sweep_path, (str(sweep_path), "?"))
@@ -651,12 +652,12 @@ def run_ours(args):
                      "traffic_source": (f"{traffic_src}: dram read+write per launch x {rank + 1} vectors per sweep "
                                         f"(bytes per step, like algorithmic_bytes_per_step)") if traffic else None,
                      "peak_source": peak_src, "kernel": kernel_desc,
-                     "algorithmic_bytes_per_step": bytes_["sweeps"], "launch_groups": int(sweep_launches),
+                     "algorithmic_bytes_per_step": bytes_["sweeps"], "per_gpu": True, "launch_groups": int(sweep_launches),
                      "share_of_step": sweep_ms / ms_profiled if ms_profiled else None,
                      "frac_of_measured_traffic": (traffic * args.steps / (sweep_ms / 1e3) / 1e9 / peak)
                      if traffic and sweep_ms > 0 else None,
-                     "whole_step_GBps": bytes_["total"] * it_per_s / 1e9,
-                     "whole_step_frac": bytes_["total"] * it_per_s / 1e9 / peak},
+                     "whole_step_GBps": bytes_["total"] / args.gpus * it_per_s / 1e9,
+                     "whole_step_frac": bytes_["total"] / args.gpus * it_per_s / 1e9 / peak},
         "kernel_ms_per_step": {"column_sweeps": sweep_ms / args.steps, "q_init": qinit_ms / args.steps,
                                "e_refresh": refresh_ms / args.steps, "streaming_level": stream_ms / args.steps,
                                "gather_level": gather_ms / args.steps,
