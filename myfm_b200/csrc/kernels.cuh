@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256)
 // FULL: K == 32 * KPL exactly (K = 32, 64): no per-lane predicate, the row stride is a compile-time constant and the
 // address of a V row is one IMAD.WIDE.  The per-row term is accumulated as q^2 - s and halved once at the end
 // (scaling by a power of two commutes with every rounding of the sum): 1177 -> ~550 instructions per tile of 32
-// rows for K = 32, L = 2 — the kernel is issue-bound (profiles/r02f_predict_tile.md).
+// rows for K = 32, L = 2 — the kernel is issue-bound (profiles/r02g_predict_tile.md).
 template <typename Real, int L, bool UNIT, int KPL, bool PAIR, bool FULL>
 __global__ void __launch_bounds__(256)
     k_predict_tile(int n_rows, const int *__restrict__ idx, const Real *__restrict__ val,
