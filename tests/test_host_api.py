@@ -171,3 +171,68 @@ def test_import_myfm_drop_in():
     assert MyFMRegressor is myfm_b200.MyFMRegressor and myfm.gibbs is myfm_b200.gibbs
     assert set(myfm.__all__) >= {"RelationBlock", "MyFMOrderedProbit", "MyFMRegressor", "MyFMClassifier",
                                  "MyFMGibbsRegressor", "MyFMGibbsClassifier"}
+
+
+def test_create_train_fm_loop_order_with_observer_callbacks(monkeypatch):
+    """The per-iteration protocol of create_train_fm (FMTrainer.hpp:56-87) on a recording stand-in for the
+    device trainer: step -> kept-sample copy -> hyper fetch -> callback; an `observer` callback has the next
+    sweep queued before it runs, a stop request ends the loop, and no sweep is ever observed twice."""
+    from myfm_b200 import _myfm
+
+    log = []
+
+    class FakeTrainer:
+        def __init__(self, X, relations, y, seed, config):
+            self.dim_all, self.n_cutpoint_groups, self.steps = 3, 0, 0
+
+        def init_fm(self, rank, init_std):
+            log.append("init")
+
+        def step(self, n):
+            self.steps += n
+            log.append(f"step{self.steps}")
+
+        def snapshot(self):
+            log.append(f"snap{self.steps}")
+            return self.steps
+
+        def get_hyper(self):
+            log.append(f"hyper{self.steps}")
+            return self.steps
+
+        def sync(self):
+            log.append("sync")
+
+    monkeypatch.setattr(_myfm, "_TrainerHandle", FakeTrainer)
+    monkeypatch.delenv("MYFM_B200_NO_RUN_AHEAD", raising=False)
+    monkeypatch.delenv("MYFM_NO_RUN_AHEAD", raising=False)
+    config = ConfigBuilder().set_identical_groups(3).set_n_iter(4).set_n_kept_samples(2).build()
+
+    def run(observer, stop_at=None):
+        log.clear()
+        seen = []
+
+        def callback(i, fm, hyper, history):
+            log.append(f"cb{i}")
+            seen.append((i, hyper, len(history.hypers)))
+            return stop_at == i
+
+        if observer is not None:
+            callback.observer = observer
+        predictor, history = _myfm.create_train_fm(2, 0.1, None, [], None, 0, config, callback)
+        return list(log), seen, predictor.samples, history.hypers
+
+    plain = run(None)
+    assert plain[0] == ["init", "step1", "hyper1", "cb0", "step2", "hyper2", "cb1", "step3", "snap3", "hyper3", "cb2",
+                        "step4", "snap4", "hyper4", "cb3", "sync"]
+    ahead = run(True)
+    assert ahead[0] == ["init", "step1", "hyper1", "step2", "cb0", "hyper2", "step3", "cb1", "snap3", "hyper3",
+                        "step4", "cb2", "snap4", "hyper4", "cb3", "sync"]
+    assert plain[1:] == ahead[1:] == run(lambda i: i % 2 == 0)[1:]  # same callbacks, kept samples, history
+    assert plain[1] == [(0, 1, 1), (1, 2, 2), (2, 3, 3), (3, 4, 4)] and plain[2] == [3, 4]
+    # a stop request: same callbacks and samples; the observer variant ran one unobserved sweep ahead
+    stop_plain, stop_ahead = run(None, stop_at=2), run(True, stop_at=2)
+    assert stop_plain[1:] == stop_ahead[1:] and stop_plain[2] == [3]
+    assert stop_plain[0][-3:] == ["hyper3", "cb2", "sync"] and stop_ahead[0][-4:] == ["hyper3", "step4", "cb2", "sync"]
+    monkeypatch.setenv("MYFM_B200_NO_RUN_AHEAD", "1")
+    assert run(True)[0] == plain[0]
