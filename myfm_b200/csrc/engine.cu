@@ -1682,7 +1682,6 @@ template <typename Real> struct Trainer : TrainerBase {
     if (peer_ok && std::getenv("MYFM_PEER_TRACE")) {
       peer_trace_buf.alloc(static_cast<size_t>(PEER_TRACE_RECORDS) * PEER_TRACE_SLOTS);
       peer_trace_buf.zero(stream);
-
     }
     MYFM_CUDA(cudaStreamSynchronize(stream));
     if (!peer_ok)
