@@ -33,6 +33,19 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str, partition
         assert ctx.world_size == world and ctx.rank == rank and ctx.n_rows_global == X.shape[0]
         np.save(os.path.join(out_dir, f"levels_{rank}.npy"), ctx.column_level)
         np.save(os.path.join(out_dir, f"rows_{rank}.npy"), ctx.rows)
+        # the engine options a trainer of this shard is created under: the same description (and the same
+        # communicator id: trainers of one context share it) every time the context is used
+        from myfm_b200.options import get_options
+
+        seen = []
+        for _ in range(2):
+            with ctx.options(dtype="f32"):
+                o = get_options()
+                seen.append((o.world_size, o.rank, o.n_rows_global, o.nccl_unique_id, o.dtype))
+                assert np.array_equal(o.row_ids, ctx.rows) and np.array_equal(o.column_level, ctx.column_level)
+        assert seen[0] == seen[1] == (world, rank, X.shape[0], None, "f32")
+        ctx.fresh_communicator()  # no NCCL id in this context: a no-op
+        assert ctx.nccl_unique_id is None
     finally:
         dist.destroy_process_group()
 
